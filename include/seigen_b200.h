@@ -1,0 +1,134 @@
+/* seigen_b200 -- C ABI of the B200-native ElasticLF4 explicit velocity-stress update.
+ *
+ * This is the boundary a host binding (ctypes in seigen_b200/capi.py) talks to.
+ * It replaces, for the explicit ElasticLF4 path of devitocodes/seigen only, what the reference
+ * obtains from Firedrake / PyOP2 / PETSc at run time.  Citations are relative to the reference
+ * repository (seigen/elastic.py unless another file is named).
+ *
+ * Conventions
+ *   - every function returns SG_OK (0) or a negative SG_E* code; sg_last_error() returns a
+ *     thread-local, human readable message for the last failure on the calling thread;
+ *   - the caller owns every host array; the library copies what it needs before returning and
+ *     keeps no host pointer;
+ *   - an sg_solver owns its device memory, stream, events and CUDA graphs.  One solver must not be
+ *     used from two threads at once; distinct solvers are independent;
+ *   - fields cross the boundary in Firedrake's dat.data layout: velocity u[cell*nd + node][i],
+ *     stress s[cell*nd + node][i][j], C-contiguous float64.  Inside the library
+ *     they live in a tile-blocked SoA layout;
+ *   - there is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef SEIGEN_B200_H
+#define SEIGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_OK 0
+#define SG_EINVAL (-1)   /* bad argument / unsupported (dim, degree) */
+#define SG_ECUDA (-2)    /* a CUDA runtime call failed */
+#define SG_ESTATE (-3)   /* call made in the wrong state (e.g. stepping before materials are set) */
+
+#define SG_BOUNDARY 0x80 /* bit 7 of a facet code marks an exterior facet */
+
+typedef struct sg_solver sg_solver;
+
+/* Mesh partition handed to sg_create.  It is the facet-to-cell adjacency that stands in for
+ * PyOP2's cell_node_map / interior_facet_node_map / exterior_facet_node_map (the maps every
+ * par_loop of ExplicitElasticLF4.solve, elastic.py:358-367, is driven by) plus the affine
+ * geometry TSFC would recompute from the coordinate field in every kernel. */
+typedef struct sg_mesh_desc {
+  int32_t dim;          /* 2 (triangles) or 3 (tetrahedra) */
+  int32_t degree;       /* DG polynomial degree: 1..4 in 2D, 1..3 in 3D (elastic.py:81-82) */
+  int64_t n_owned;      /* cells this solver updates */
+  int64_t n_total;      /* n_owned + halo cells; halo cells (index >= n_owned) are only read */
+  const int32_t* nbr;   /* [n_owned][dim+1] cell across facet f (own index on an exterior facet) */
+  const uint8_t* code;  /* [n_owned][dim+1] f' * dim! + s (neighbour's facet number and gluing
+                           permutation, seigen_b200/refelem.py ftab), | SG_BOUNDARY if exterior */
+  const double* jinv;   /* [n_owned][dim][dim] Jinv[r][k] = d(xi_r)/d(x_k) */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t n_boundary;   /* cells [0, n_boundary) touch a partition cut: they are updated first so the
+                           halo exchange of their values overlaps the rest (0 on a single GPU) */
+} sg_mesh_desc;
+
+/* Which device field sg_get_field / sg_field_ptr address. */
+#define SG_FIELD_U 0   /* u0 / u1      (elastic.py:98, 102) */
+#define SG_FIELD_S 1   /* s0 / s1      (elastic.py:93, 97)  */
+#define SG_FIELD_UH 2  /* uh1 / utemp  (elastic.py:99-100)  -- scratch velocity */
+#define SG_FIELD_SH 3  /* stemp / sh1  (elastic.py:95, 94)  -- scratch stress   */
+
+/* Which cells a stage launch covers (multi-GPU overlap). */
+#define SG_PART_ALL 0
+#define SG_PART_BOUNDARY 1
+#define SG_PART_INTERIOR 2
+
+const char* sg_last_error(void);
+int sg_version(void);
+
+/* ElasticLF4.__init__ (elastic.py:66-124): allocates u0/s0 and the two scratch fields on the device. */
+int sg_create(sg_solver** out, const sg_mesh_desc* desc);
+void sg_destroy(sg_solver* h);
+
+/* Plain attributes elastic.density / .l / .mu (tests/eigenmode/eigenmode_2d.py:17-20).  lam_cell / mu_cell
+ * are optional per-cell values [n_owned]; NULL = use the scalars. */
+int sg_set_material(sg_solver* h, double density, double lam, double mu,
+                    const double* lam_cell, const double* mu_cell);
+
+/* elastic.absorption (elastic.py:136-141, term elastic.py:207-208).  For each listed cell the caller passes
+ * the nd x nd matrix A = sum_b sigma_b * Minv * T[:, b, :] so that P(sigma, u)_i = A u_i.  n = 0 clears. */
+int sg_set_absorption(sg_solver* h, int64_t n, const int64_t* cell, const double* mats);
+
+/* elastic.source (elastic.py:149-154, 285-288): nodal source values.  sdof[k] indexes the stress field in
+ * boundary layout, amp[step][k] is the value interpolated at the END time of step `step` (0-based).
+ * nsrc = 0 clears. */
+int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nsteps, const double* amp);
+
+/* u0.assign / s0.assign (tests/explosive_source/explosive_source_lf4.py:48-52); arrays are [n_total*nd][d] and
+ * [n_total*nd][d][d].  Either pointer may be NULL (field left unchanged). */
+int sg_set_state(sg_solver* h, const double* u, const double* s);
+/* u1.dat.data / s1.dat.data after run (elastic.py:315).  Synchronises with all queued work. */
+int sg_get_state(sg_solver* h, double* u, double* s);
+int sg_get_field(sg_solver* h, int which, double* out);
+
+/* The loop body of ElasticLF4.run (elastic.py:283-304) `nsteps` times, starting at 0-based step index
+ * `first_step` (only used to index the source table).  Work is queued on the solver's stream; the call
+ * returns without waiting (sg_get_state / sg_synchronize wait). */
+int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step);
+int sg_synchronize(sg_solver* h);
+/* Device time in milliseconds between the start and the end of the last sg_step call (CUDA events on the
+ * solver's stream); synchronises. */
+int sg_last_step_ms(sg_solver* h, double* ms);
+
+/* One of the six fused passes (K1 uh1, K2 stemp, K3 u1, K4 sh1, K5 utemp, K6 s1), on all cells or on
+ * the boundary / interior part.  Used by per-stage parity tests and by the multi-GPU driver, which exchanges
+ * halos between stages.  `step` indexes the source table. */
+int sg_stage(sg_solver* h, int stage, int part, double dt, int64_t step);
+
+/* Multi-GPU plumbing.  Halo exchange moves whole cells in device (tile-blocked) layout:
+ * sg_set_halo_plan registers the owned cells whose values neighbours need, grouped by destination;
+ * sg_pack gathers field `which` of those cells into a contiguous device buffer (cell-major, K doubles per
+ * cell); sg_unpack scatters a received buffer into halo cells [n_owned + first, n_owned + first + count).
+ * Buffers are device pointers owned by the caller (e.g. torch tensors used with torch.distributed). */
+int sg_set_halo_plan(sg_solver* h, int64_t nsend, const int64_t* send_cells);
+int sg_pack(sg_solver* h, int which, double* dst, int on_comm_stream);
+int sg_unpack(sg_solver* h, int which, const double* src, int64_t first, int64_t count, int on_comm_stream);
+/* Stream ordering helpers for the overlap schedule: the solver has a compute and a comm stream. */
+int sg_comm_wait_compute(sg_solver* h);   /* comm stream waits for everything queued on compute */
+int sg_compute_wait_comm(sg_solver* h);   /* compute stream waits for everything queued on comm */
+void* sg_stream(sg_solver* h, int comm);  /* cudaStream_t, for torch.cuda.ExternalStream */
+void* sg_field_ptr(sg_solver* h, int which);
+
+/* Sizes, so that a binding can allocate: nd nodes per cell, tile (cells per device tile). */
+int sg_nodes_per_cell(int dim, int degree);
+int sg_tile_cells(int dim, int degree);
+
+/* Page-locked host buffers for sg_set_state / sg_get_state (optional; any host pointer works). */
+void* sg_host_alloc(int64_t bytes);
+void sg_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEIGEN_B200_H */

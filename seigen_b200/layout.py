@@ -1,0 +1,186 @@
+"""Cell ordering, partitioning and halo plans for the device layout.
+
+PyOP2 iterates cells in DMPlex order and finds facet neighbours through indirection maps; the
+stage kernels instead want *tiles* of consecutive cells that are compact in space, so that most
+facet neighbours of a tile's cells sit in the same shared-memory tile.  This module
+
+* orders cells along a Hilbert curve through their centroids (``hilbert_order``);
+* splits the mesh over ranks (recursive coordinate bisection or METIS, ``partition_cells``) -
+  the role DMPlex distribution plays for the reference's MPI runs;
+* builds, for one rank, the local numbering ``[cut-adjacent cells | other owned cells | halo cells
+  grouped by owner]`` with its send lists (``build_rank_plan``) - the one-layer DG halo PyOP2
+  exchanges around every par_loop.
+
+Everything here is host-side NumPy and deterministic: every rank can rebuild every other rank's
+plan from the global ``(coords, cells)`` arrays.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .mesh import BOUNDARY, Mesh, Topology
+
+__all__ = ["hilbert_key", "hilbert_order", "partition_cells", "RankPlan", "build_rank_plan"]
+
+
+def hilbert_key(points: np.ndarray, bits: int | None = None) -> np.ndarray:
+    """Hilbert-curve index (uint64) of each point (n, d); Skilling's transpose algorithm, vectorised."""
+    pts = np.asarray(points, dtype=np.float64)
+    n, d = pts.shape
+    if bits is None:
+        bits = 63 // d if d > 1 else 62
+        bits = min(bits, 20)
+    lo = pts.min(axis=0)
+    span = pts.max(axis=0) - lo
+    span[span == 0] = 1.0
+    scale = ((1 << bits) - 1) / span.max()
+    X = np.floor((pts - lo) * scale).astype(np.uint64).T.copy()      # (d, n)
+    if d == 1:
+        return X[0]
+    M = np.uint64(1 << (bits - 1))
+    Q = M
+    one = np.uint64(1)
+    while Q > one:
+        P = Q - one
+        for i in range(d):
+            hit = (X[i] & Q) != 0
+            t = (X[0] ^ X[i]) & P
+            X0_new = np.where(hit, X[0] ^ P, X[0] ^ t)
+            if i != 0:
+                X[i] = np.where(hit, X[i], X[i] ^ t)
+            X[0] = X0_new
+        Q >>= one
+    for i in range(1, d):
+        X[i] ^= X[i - 1]
+    t = np.zeros(n, dtype=np.uint64)
+    Q = M
+    while Q > one:
+        t = np.where((X[d - 1] & Q) != 0, t ^ (Q - one), t)
+        Q >>= one
+    for i in range(d):
+        X[i] ^= t
+    key = np.zeros(n, dtype=np.uint64)
+    for b in range(bits - 1, -1, -1):
+        for i in range(d):
+            key = (key << one) | ((X[i] >> np.uint64(b)) & one)
+    return key
+
+
+def hilbert_order(centroids: np.ndarray) -> np.ndarray:
+    """Permutation ``order`` such that ``centroids[order]`` walks a Hilbert curve (stable)."""
+    return np.argsort(hilbert_key(centroids), kind="stable")
+
+
+def _rcb(centroids, ids, nparts, out, first):
+    if nparts == 1:
+        out[ids] = first
+        return
+    left_parts = nparts // 2
+    c = centroids[ids]
+    axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+    k = int(round(len(ids) * left_parts / nparts))
+    order = np.argsort(c[:, axis], kind="stable")
+    _rcb(centroids, ids[order[:k]], left_parts, out, first)
+    _rcb(centroids, ids[order[k:]], nparts - left_parts, out, first + left_parts)
+
+
+def partition_cells(mesh: Mesh, nparts: int, method: str = "rcb") -> np.ndarray:
+    """Owner rank of every cell.  ``rcb``: recursive coordinate bisection (cut = planes for box meshes)."""
+    E = mesh.num_cells()
+    part = np.zeros(E, dtype=np.int32)
+    if nparts <= 1:
+        return part
+    if method == "rcb":
+        _rcb(mesh.cell_centroids(), np.arange(E), nparts, part, 0)
+        return part
+    if method == "metis":
+        from .partition_metis import metis_partition
+        return metis_partition(mesh.topology, nparts)
+    raise ValueError("method must be 'rcb' or 'metis'")
+
+
+@dataclass
+class RankPlan:
+    """Local numbering of one rank (all arrays index / hold GLOBAL cell ids unless noted)."""
+    rank: int
+    nranks: int
+    local_to_global: np.ndarray            # (n_total,)  owned cells first, then halo
+    n_owned: int
+    n_boundary: int                        # owned cells [0, n_boundary) touch the cut
+    nbr: np.ndarray                        # (n_owned, nf) LOCAL neighbour index
+    code: np.ndarray                       # (n_owned, nf)
+    jinv: np.ndarray                       # (n_owned, d, d)
+    recv: dict = field(default_factory=dict)   # peer -> (first halo slot, count)   [slots relative to n_owned]
+    send: dict = field(default_factory=dict)   # peer -> LOCAL owned cell ids, in the peer's halo order
+    send_cells: np.ndarray | None = None       # concatenation of ``send`` in ascending peer order
+    send_offsets: dict = field(default_factory=dict)   # peer -> (offset, count) into send_cells
+
+    @property
+    def n_total(self):
+        return len(self.local_to_global)
+
+    @property
+    def n_halo(self):
+        return self.n_total - self.n_owned
+
+
+def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> RankPlan:
+    topo: Topology = mesh.topology
+    E, nf = topo.nbr.shape
+    part = np.asarray(part)
+    owned_mask = part == rank
+    owned = np.flatnonzero(owned_mask)
+    if len(owned) == 0:
+        raise ValueError(f"rank {rank} owns no cells")
+    nb = topo.nbr[owned]                                          # global neighbour ids
+    nb_part = part[nb]
+    remote = nb_part != rank                                      # (n_owned, nf); exterior facets point to self
+    is_bnd = remote.any(axis=1)
+
+    cent = mesh.cell_centroids()
+    key = hilbert_key(cent)                                       # one global curve: consistent across ranks
+    o_b = owned[is_bnd]
+    o_i = owned[~is_bnd]
+    o_b = o_b[np.argsort(key[o_b], kind="stable")]
+    o_i = o_i[np.argsort(key[o_i], kind="stable")]
+    owned_sorted = np.concatenate([o_b, o_i])
+
+    # halo: remote cells across a facet of an owned cell, grouped by owner, ascending global id inside a group
+    halo_ids = np.unique(nb[remote])
+    halo_owner = part[halo_ids]
+    order = np.lexsort((halo_ids, halo_owner))
+    halo_ids, halo_owner = halo_ids[order], halo_owner[order]
+    recv = {}
+    for q in np.unique(halo_owner):
+        sel = np.flatnonzero(halo_owner == q)
+        recv[int(q)] = (int(sel[0]), int(len(sel)))
+
+    l2g = np.concatenate([owned_sorted, halo_ids]).astype(np.int64)
+    g2l = np.full(E, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(len(l2g))
+
+    nbr_local = g2l[topo.nbr[owned_sorted]]
+    assert (nbr_local >= 0).all()
+    code = topo.code[owned_sorted].copy()
+    jinv = np.ascontiguousarray(topo.jinv[owned_sorted])
+
+    # send lists: my cells that peer q sees across its facets = my cut-adjacent cells with a neighbour owned by q,
+    # in ascending global id (the order q's halo group uses)
+    send, send_offsets, chunks, off = {}, {}, [], 0
+    nb_b = topo.nbr[o_b]
+    pb = part[nb_b]
+    for q in sorted(recv):
+        mine = np.unique(o_b[(pb == q).any(axis=1)])
+        loc = g2l[mine]
+        send[q] = loc
+        send_offsets[q] = (off, len(loc))
+        chunks.append(loc)
+        off += len(loc)
+    send_cells = np.concatenate(chunks).astype(np.int64) if chunks else np.zeros(0, dtype=np.int64)
+
+    return RankPlan(rank=rank, nranks=nranks, local_to_global=l2g, n_owned=len(owned_sorted),
+                    n_boundary=len(o_b), nbr=np.ascontiguousarray(nbr_local.astype(np.int32)),
+                    code=np.ascontiguousarray(code.astype(np.uint8)), jinv=jinv, recv=recv, send=send,
+                    send_cells=send_cells, send_offsets=send_offsets)
