@@ -51,6 +51,10 @@ typedef struct sg_mesh_desc {
   int32_t device;       /* CUDA device ordinal */
   int32_t n_boundary;   /* cells [0, n_boundary) touch a partition cut: they are updated first so the
                            halo exchange of their values overlaps the rest (0 on a single GPU) */
+  int32_t geom_classes; /* 1: cells whose Jinv agree to 2^-36 relative (translates of one another on uniform
+                           meshes) share one geometry record, saving dim*dim*8 B of HBM traffic per cell per
+                           pass; falls back to per-cell geometry above 4096 classes.  0: always per cell */
+  int32_t reserved;
 } sg_mesh_desc;
 
 /* Which device field sg_get_field / sg_field_ptr address. */
@@ -105,6 +109,10 @@ int sg_last_step_ms(sg_solver* h, double* ms);
  * the boundary / interior part.  Used by per-stage parity tests and by the multi-GPU driver, which exchanges
  * halos between stages.  `step` indexes the source table. */
 int sg_stage(sg_solver* h, int stage, int part, double dt, int64_t step);
+
+/* Measurement aid: `reps` back-to-back launches of one stage's kernel on the solver's stream between two CUDA
+ * events; *ms_avg = elapsed / reps.  The state is advanced as a side effect. */
+int sg_time_stage(sg_solver* h, int stage, int part, double dt, int reps, double* ms_avg);
 
 /* Multi-GPU plumbing.  Halo exchange moves whole cells in device (tile-blocked) layout:
  * sg_set_halo_plan registers the owned cells whose values neighbours need, grouped by destination;

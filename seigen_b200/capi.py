@@ -35,6 +35,8 @@ class MeshDesc(C.Structure):
         ("jinv", C.c_void_p),
         ("device", C.c_int32),
         ("n_boundary", C.c_int32),
+        ("geom_classes", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -54,6 +56,7 @@ _SIGNATURES = {
     "sg_synchronize": (C.c_int, [_P]),
     "sg_last_step_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "sg_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int64]),
+    "sg_time_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "sg_set_halo_plan": (C.c_int, [_P, C.c_int64, _P]),
     "sg_pack": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "sg_unpack": (C.c_int, [_P, C.c_int, _P, C.c_int64, C.c_int64, C.c_int]),

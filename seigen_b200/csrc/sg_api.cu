@@ -4,8 +4,10 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -27,7 +29,7 @@ int fail(int code, const std::string& msg) {
 
 // ---- per-element kernel configuration ------------------------------------------------------
 struct Variant {
-  int dim, degree, nd, nfp, tile, split;
+  int dim, degree, nd, nfp, tile, split, minb;
   size_t smem_f, smem_g;
   const void* f_plain;
   const void* f_axpy;
@@ -35,7 +37,7 @@ struct Variant {
   const void* g_axpy;
 };
 
-template <int D, int P, int TILE, int SPLIT> Variant make_variant() {
+template <int D, int P, int TILE, int SPLIT, int MINB> Variant make_variant() {
   using E = ElemOps<D, P>;
   using L = sg::SmemLayout<D, P, TILE>;
   Variant v;
@@ -45,28 +47,48 @@ template <int D, int P, int TILE, int SPLIT> Variant make_variant() {
   v.nfp = E::NFP;
   v.tile = TILE;
   v.split = SPLIT;
+  v.minb = MINB;
   v.smem_f = L::f_bytes;
   v.smem_g = L::g_bytes;
-  v.f_plain = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, false>;
-  v.f_axpy = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, true>;
-  v.g_plain = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, false>;
-  v.g_axpy = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, true>;
+  v.f_plain = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, false>;
+  v.f_axpy = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, true>;
+  v.g_plain = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, false>;
+  v.g_axpy = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, true>;
   return v;
 }
 
 const std::vector<Variant>& variants() {
   static const std::vector<Variant> v = {
-      make_variant<2, 1, 64, 1>(), make_variant<2, 2, 64, 1>(), make_variant<2, 3, 64, 1>(),
-      make_variant<2, 4, 32, 1>(), make_variant<3, 1, 64, 1>(), make_variant<3, 2, 32, 3>(),
-      make_variant<3, 3, 32, 3>(),
+      // first entry of each (dim, degree) is the default; the others are tuning candidates selectable with
+      // SG_TILE / SG_SPLIT / SG_MINB (scripts/perf_probe.py)
+      make_variant<2, 1, 64, 1, 12>(), make_variant<2, 1, 64, 1, 16>(), make_variant<2, 1, 128, 1, 6>(),
+      make_variant<2, 1, 128, 1, 8>(),
+      make_variant<2, 2, 64, 1, 10>(), make_variant<2, 2, 64, 1, 12>(), make_variant<2, 2, 64, 1, 16>(),
+      make_variant<2, 2, 128, 1, 5>(), make_variant<2, 2, 128, 1, 6>(), make_variant<2, 2, 32, 1, 20>(),
+      make_variant<2, 3, 64, 1, 8>(),
+      make_variant<2, 4, 32, 1, 6>(),
+      make_variant<3, 1, 64, 1, 8>(), make_variant<3, 1, 64, 1, 12>(), make_variant<3, 1, 32, 1, 16>(),
+      make_variant<3, 2, 32, 3, 4>(),
+      make_variant<3, 3, 32, 3, 2>(),
   };
   return v;
 }
 
+int env_int(const char* name) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : 0;
+}
+
 const Variant* find_variant(int dim, int degree) {
-  for (const Variant& v : variants())
-    if (v.dim == dim && v.degree == degree) return &v;
-  return nullptr;
+  const int tile = env_int("SG_TILE"), split = env_int("SG_SPLIT"), minb = env_int("SG_MINB");
+  const Variant* first = nullptr;
+  for (const Variant& v : variants()) {
+    if (v.dim != dim || v.degree != degree) continue;
+    if (!first) first = &v;
+    if ((tile == 0 || v.tile == tile) && (split == 0 || v.split == split) && (minb == 0 || v.minb == minb))
+      return &v;
+  }
+  return first;
 }
 
 template <class T> struct DevBuf {
@@ -94,7 +116,9 @@ struct sg_solver {
   int64_t n_owned = 0, n_total = 0, n_owned_pad = 0, n_halo = 0, n_dev = 0, n_boundary = 0;
   int tiles_owned = 0, tiles_total = 0, tiles_boundary = 0;
   DevBuf<double> u, s, uh, sh;          // state + scratch, tile-blocked
-  DevBuf<double> geo, lam, mu, absmat, amp;
+  DevBuf<double> geo, geotab, lam, mu, absmat, amp;
+  DevBuf<uint16_t> geoidx;
+  int64_t n_geo_classes = 0;
   DevBuf<int32_t> nbr, absidx;
   DevBuf<uint8_t> code;
   DevBuf<int64_t> src_addr, step_dev, send_cells;
@@ -129,6 +153,8 @@ sg::StageParams base_params(sg_solver* h) {
   sg::StageParams p;
   std::memset(&p, 0, sizeof(p));
   p.geo = h->geo.p;
+  p.geoidx = h->geoidx.p;
+  p.geotab = h->geotab.p;
   p.nbr = h->nbr.p;
   p.code = h->code.p;
   p.absidx = h->nabs_pad > 0 ? h->absidx.p : nullptr;
@@ -344,15 +370,73 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   }
   SG_CUDA_H(h->nbr.alloc(nbr.size()));
   SG_CUDA_H(h->code.alloc(code.size()));
-  SG_CUDA_H(h->geo.alloc(geo.size()));
   SG_CUDA_H(cudaMemcpy(h->nbr.p, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
   SG_CUDA_H(cudaMemcpy(h->code.p, code.data(), code.size(), cudaMemcpyHostToDevice));
-  SG_CUDA_H(cudaMemcpy(h->geo.p, geo.data(), geo.size() * 8, cudaMemcpyHostToDevice));
 
-  for (const void* fn : {v->f_plain, v->f_axpy})
+  // Geometry classes: on (piecewise) uniform meshes thousands of cells are translates of one another and share
+  // Jinv up to the round-off of the vertex coordinates.  Such cells get a 2-byte class id instead of D*D doubles
+  // (32-72 B of HBM traffic per cell per pass).  Classes are merged only within SG_GEOM_TOL relative.
+  bool use_classes = false;
+  if (d->geom_classes) {
+    std::unordered_map<std::string, uint16_t> seen;
+    std::vector<double> tab;
+    std::vector<uint16_t> gi(npad, 0);
+    const size_t max_classes = 4096;
+    use_classes = true;
+    for (int64_t e = 0; e < h->n_owned && use_classes; ++e) {
+      const double* J = d->jinv + (size_t)e * dd;
+      double nrm = 0.0;
+      for (int k = 0; k < dd; ++k) nrm = std::fmax(nrm, std::fabs(J[k]));
+      int ex = 0;
+      std::frexp(nrm, &ex);
+      const double q = std::ldexp(1.0, ex - 36);   // quantum: 2^-36 of the largest entry (~1.5e-11 relative)
+      int64_t key[10];
+      key[0] = ex;
+      for (int k = 0; k < dd; ++k) key[1 + k] = (int64_t)std::llround(J[k] / q);
+      std::string ks((const char*)key, sizeof(int64_t) * (1 + dd));
+      auto it = seen.find(ks);
+      uint16_t cls;
+      if (it == seen.end()) {
+        if (seen.size() >= max_classes) {
+          use_classes = false;
+          break;
+        }
+        cls = (uint16_t)seen.size();
+        seen.emplace(ks, cls);
+        tab.insert(tab.end(), J, J + dd);
+      } else {
+        cls = it->second;
+      }
+      const size_t t = (size_t)e / T, l = (size_t)e % T;
+      gi[t * T + l] = cls;
+    }
+    if (use_classes) {
+      // padding lanes need a zero Jinv: give them their own class
+      if (npad > (size_t)h->n_owned) {
+        const uint16_t zc = (uint16_t)(tab.size() / dd);
+        tab.insert(tab.end(), dd, 0.0);
+        for (size_t e = (size_t)h->n_owned; e < npad; ++e) gi[e] = zc;
+      }
+      h->n_geo_classes = (int64_t)(tab.size() / dd);
+      SG_CUDA_H(h->geoidx.alloc(gi.size()));
+      SG_CUDA_H(h->geotab.alloc(tab.size()));
+      SG_CUDA_H(cudaMemcpy(h->geoidx.p, gi.data(), gi.size() * 2, cudaMemcpyHostToDevice));
+      SG_CUDA_H(cudaMemcpy(h->geotab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  if (!use_classes) {
+    SG_CUDA_H(h->geo.alloc(geo.size()));
+    SG_CUDA_H(cudaMemcpy(h->geo.p, geo.data(), geo.size() * 8, cudaMemcpyHostToDevice));
+  }
+
+  for (const void* fn : {v->f_plain, v->f_axpy}) {
     SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem_f));
-  for (const void* fn : {v->g_plain, v->g_axpy})
+    SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  for (const void* fn : {v->g_plain, v->g_axpy}) {
     SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem_g));
+    SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   SG_CUDA_H(cudaStreamSynchronize(h->stream));
 #undef SG_CUDA_H
   *out = h;
@@ -366,7 +450,7 @@ void sg_destroy(sg_solver* h) {
   if (h->comm) cudaStreamSynchronize(h->comm);
   drop_graph(h);
   h->u.release(); h->s.release(); h->uh.release(); h->sh.release();
-  h->geo.release(); h->lam.release(); h->mu.release(); h->absmat.release(); h->amp.release();
+  h->geo.release(); h->geotab.release(); h->geoidx.release(); h->lam.release(); h->mu.release(); h->absmat.release(); h->amp.release();
   h->nbr.release(); h->absidx.release(); h->code.release();
   h->src_addr.release(); h->step_dev.release(); h->send_cells.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -561,6 +645,25 @@ int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
   SG_CUDA(cudaEventRecord(h->ev0, st));
   for (int64_t n = 0; n < nsteps; ++n) SG_CUDA(cudaGraphLaunch(h->graph, st));
   SG_CUDA(cudaEventRecord(h->ev1, st));
+  return SG_OK;
+}
+
+int sg_time_stage(sg_solver* h, int stage, int part, double dt, int reps, double* ms_avg) {
+  if (!h || !ms_avg || reps <= 0) return fail(SG_EINVAL, "sg_time_stage: bad arguments");
+  if (!h->have_material) return fail(SG_ESTATE, "sg_time_stage: call sg_set_material first");
+  SG_CUDA(cudaSetDevice(h->device));
+  int rc = launch_stage(h, stage, part, dt, h->stream);   // warm-up launch, untimed
+  if (rc) return rc;
+  SG_CUDA(cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; ++r) {
+    rc = launch_stage(h, stage, part, dt, h->stream);
+    if (rc) return rc;
+  }
+  SG_CUDA(cudaEventRecord(h->ev1, h->stream));
+  SG_CUDA(cudaEventSynchronize(h->ev1));
+  float f = 0.f;
+  SG_CUDA(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+  *ms_avg = (double)f / reps;
   return SG_OK;
 }
 

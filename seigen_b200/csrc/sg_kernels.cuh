@@ -33,7 +33,9 @@ struct StageParams {
   const double* ax0;      // AXPY: c0 * ax0 (u0 / s0), own cells only (may alias out)
   const double* ax1;      // AXPY: c1 * ax1 (uh1 / sh1), own cells only
   const double* absu;     // F-type: velocity the sponge multiplies (u0 / u1); unused if absidx == nullptr
-  const double* geo;      // [tile][D*D][TILE]  Jinv
+  const double* geo;      // [tile][D*D][TILE]  Jinv per cell, or nullptr when geometry classes are used
+  const uint16_t* geoidx; // [tile][TILE] class of each cell (affine-congruent cells share one Jinv)
+  const double* geotab;   // [nclass][D*D]
   const int32_t* nbr;     // [tile][NF][TILE]   neighbour cell (device index)
   const uint8_t* code;    // [tile][NF][TILE]
   const int32_t* absidx;  // [tile][TILE] row of absmat or -1; nullptr = no sponge anywhere
@@ -64,6 +66,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -191,7 +196,7 @@ template <int D, int P, int TILE> struct SmemLayout {
 // ---------------------------------------------------------------------------------------------
 // common prologue: start the bulk copy of the input tile, fetch per-cell geometry meanwhile
 // ---------------------------------------------------------------------------------------------
-template <int D, int ND, int NFP, int TILE, int KIN, int NTHREADS, int FTAB_SIZE>
+template <int D, int ND, int NFP, int TILE, int KIN, int KAX, int NTHREADS, int FTAB_SIZE>
 __device__ __forceinline__ void stage_prologue(const StageParams& p, int tile, int lane, double* sIn,
                                                uint64_t* bar, unsigned char* sft, const unsigned char* ftab,
                                                FaceGeom<D, ND, NFP, TILE>& g) {
@@ -204,12 +209,24 @@ __device__ __forceinline__ void stage_prologue(const StageParams& p, int tile, i
     constexpr uint32_t BYTES = KIN * TILE * 8;
     mbar_expect_tx(bar, BYTES);
     bulk_g2s(sIn, p.in + (size_t)tile * (KIN * TILE), BYTES, bar);
+    if (KAX > 0) {   // LF4 combination operands: start their DRAM reads now, consume them from L2 in the epilogue
+      prefetch_l2(p.ax0 + (size_t)tile * (KAX * TILE), KAX * TILE * 8);
+      prefetch_l2(p.ax1 + (size_t)tile * (KAX * TILE), KAX * TILE * 8);
+    }
   }
-  const double* geo = p.geo + (size_t)tile * (D * D * TILE) + lane;
+  if (p.geoidx != nullptr) {
+    const double* gt = p.geotab + (size_t)p.geoidx[(size_t)tile * TILE + lane] * (D * D);
 #pragma unroll
-  for (int r = 0; r < D; ++r)
+    for (int r = 0; r < D; ++r)
 #pragma unroll
-    for (int k = 0; k < D; ++k) g.ji[r][k] = geo[(r * D + k) * TILE];
+      for (int k = 0; k < D; ++k) g.ji[r][k] = __ldg(gt + r * D + k);
+  } else {
+    const double* geo = p.geo + (size_t)tile * (D * D * TILE) + lane;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int k = 0; k < D; ++k) g.ji[r][k] = geo[(r * D + k) * TILE];
+  }
   const int32_t* nb = p.nbr + (size_t)tile * (NF * TILE) + lane;
   const uint8_t* cd = p.code + (size_t)tile * (NF * TILE) + lane;
 #pragma unroll
@@ -224,8 +241,8 @@ __device__ __forceinline__ void stage_prologue(const StageParams& p, int tile, i
 // F-type pass:   out_i = Dv(in)_i - A_cell * absu_i            (K1, K5)
 //                out_i = c0*ax0_i + c1*ax1_i + c2*(Dv(in)_i - A_cell*absu_i)   (K3, AXPY)
 // ---------------------------------------------------------------------------------------------
-template <int D, int P, int TILE, int SPLIT, bool AXPY>
-__global__ void __launch_bounds__(TILE* SPLIT) stage_f_kernel(const StageParams p) {
+template <int D, int P, int TILE, int SPLIT, int MINB, bool AXPY>
+__global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageParams p) {
   using E = ElemOps<D, P>;
   constexpr int ND = E::ND, NFP = E::NFP, KS = D * D * ND, KU = D * ND, IPT = D / SPLIT;
   static_assert(D % SPLIT == 0, "SPLIT must divide D");
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(TILE* SPLIT) stage_f_kernel(const StageParams 
   const int lane = threadIdx.x % TILE, ig = threadIdx.x / TILE;
   const int tile = p.tile0 + blockIdx.x;
   FaceGeom<D, ND, NFP, TILE> g;
-  stage_prologue<D, ND, NFP, TILE, KS, TILE * SPLIT, E::FTAB_SIZE>(p, tile, lane, sIn, bar, sft, E::ftab(), g);
+  stage_prologue<D, ND, NFP, TILE, KS, (AXPY ? KU : 0), TILE * SPLIT, E::FTAB_SIZE>(p, tile, lane, sIn, bar, sft, E::ftab(), g);
 
   int aidx = -1;
   if (p.absidx != nullptr) aidx = p.absidx[(size_t)tile * TILE + lane];
@@ -283,8 +300,8 @@ __global__ void __launch_bounds__(TILE* SPLIT) stage_f_kernel(const StageParams 
 // G-type pass:   out_ij = lam*delta_ij*div + mu*(G_ij + G_ji),  G_ij = d~_j in_i      (K2, K4)
 //                out_ij = c0*ax0_ij + c1*ax1_ij + c2*(...)                           (K6, AXPY)
 // ---------------------------------------------------------------------------------------------
-template <int D, int P, int TILE, int SPLIT, bool AXPY>
-__global__ void __launch_bounds__(TILE* SPLIT) stage_g_kernel(const StageParams p) {
+template <int D, int P, int TILE, int SPLIT, int MINB, bool AXPY>
+__global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageParams p) {
   using E = ElemOps<D, P>;
   constexpr int ND = E::ND, NFP = E::NFP, KS = D * D * ND, KU = D * ND, IPT = D / SPLIT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -296,7 +313,7 @@ __global__ void __launch_bounds__(TILE* SPLIT) stage_g_kernel(const StageParams 
   const int lane = threadIdx.x % TILE, ig = threadIdx.x / TILE;
   const int tile = p.tile0 + blockIdx.x;
   FaceGeom<D, ND, NFP, TILE> g;
-  stage_prologue<D, ND, NFP, TILE, KU, TILE * SPLIT, E::FTAB_SIZE>(p, tile, lane, sIn, bar, sft, E::ftab(), g);
+  stage_prologue<D, ND, NFP, TILE, KU, (AXPY ? KS : 0), TILE * SPLIT, E::FTAB_SIZE>(p, tile, lane, sIn, bar, sft, E::ftab(), g);
 
   GCtx<D, ND, NFP, TILE> c;
   c.tileU = sIn;

@@ -20,7 +20,8 @@ __all__ = ["DeviceSolver"]
 
 
 class DeviceSolver:
-    def __init__(self, mesh: Mesh, degree: int, device: int = 0, plan: RankPlan | None = None):
+    def __init__(self, mesh: Mesh, degree: int, device: int = 0, plan: RankPlan | None = None,
+                 geom_classes: bool = True):
         self.mesh = mesh
         self.dim = mesh.dim
         self.degree = int(degree)
@@ -35,7 +36,8 @@ class DeviceSolver:
         jinv = np.ascontiguousarray(plan.jinv, dtype=np.float64)
         desc = capi.MeshDesc(dim=self.dim, degree=self.degree, n_owned=plan.n_owned, n_total=plan.n_total,
                              nbr=nbr.ctypes.data, code=code.ctypes.data, jinv=jinv.ctypes.data,
-                             device=int(device), n_boundary=int(plan.n_boundary))
+                             device=int(device), n_boundary=int(plan.n_boundary),
+                             geom_classes=int(bool(geom_classes)), reserved=0)
         check(lib.sg_create(C.byref(self._h), C.byref(desc)))
         self.n_owned = plan.n_owned
         self.n_total = plan.n_total
@@ -159,6 +161,11 @@ class DeviceSolver:
 
     def stage(self, stage, dt, step=0, part=capi.PART_ALL):
         check(lib.sg_stage(self._h, int(stage), int(part), float(dt), int(step)))
+
+    def time_stage(self, stage, dt, reps=10, part=capi.PART_ALL):
+        ms = C.c_double()
+        check(lib.sg_time_stage(self._h, int(stage), int(part), float(dt), int(reps), C.byref(ms)))
+        return ms.value
 
     def synchronize(self):
         check(lib.sg_synchronize(self._h))

@@ -1,0 +1,303 @@
+"""``ElasticLF4`` with the reference's constructor / attribute / ``run(T)`` interface, running on B200.
+
+Mirror of ``seigen/elastic.py`` for the explicit path only.  ``ElasticLF4.create(mesh, family, degree,
+dimension, solver, output)`` (elastic.py:27-64) returns an object on which callers set the plain attributes
+``density, dt, mu, l``, optionally ``absorption_function`` + ``absorption`` and ``source_expression`` +
+``source_function`` + ``source`` (elastic.py:136-154), assign ``u0`` / ``s0`` and call ``run(T)`` which
+returns ``(u1, s1)`` (elastic.py:267-315).
+
+What differs underneath: the reference turns each of its eight UFL forms (elastic.py:156-202, 341-352) into
+par_loops and calls ``solve`` eight times per step; per-form ``solve()`` is the wrong granularity for fusion,
+so this class pattern-matches the fixed LF4 scheme and hands whole time steps to the C ABI
+(``include/seigen_b200.h``): six fused passes per step, replayed from a CUDA graph on one GPU, or driven stage
+by stage with halo exchanges between ranks.  ``solver`` strings ``explicit | parloop | fusion | tiling`` all
+select this path (the reference defines their results to agree to rtol 1e-10,
+tests/tiling/explosive_source.py:659-660); ``implicit`` (global KSP solves, elastic.py:318-332) is out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib, ptr
+from .compat import (File, Function, FunctionSpace, TensorFunctionSpace, VectorFunctionSpace, mesh_plan,
+                     timed_region)
+from .device import DeviceSolver
+from .helpers import log
+
+__all__ = ["ElasticLF4", "ExplicitElasticLF4", "step_times"]
+
+
+def step_times(T, dt):
+    """Values taken by ``t`` in ``t = dt; while t <= T + 1e-12: ...; t += dt`` (elastic.py:279-280, 313)."""
+    out = []
+    t = dt
+    while t <= T + 1e-12:
+        out.append(t)
+        t += dt
+    return out
+
+
+class ElasticLF4(object):
+    """Elastic wave equation solver: DG in space, fourth-order leap-frog in time (see module docstring)."""
+
+    @staticmethod
+    def create(mesh, family, degree, dimension, solver="explicit", output=True):
+        if solver == "implicit":
+            raise NotImplementedError("solver='implicit' (PETSc KSP solves, seigen/elastic.py:318-332) is outside "
+                                      "the B200 hot path; use 'explicit'")
+        elif solver in ("explicit", "parloop", "fusion", "tiling"):
+            return ExplicitElasticLF4(mesh, family, degree, dimension, output=output)
+        else:
+            raise ValueError("Unknown solver mode. Must be one of: implicit, explicit, parloop")
+
+    def __init__(self, mesh, family, degree, dimension, output=True):
+        with timed_region('function setup'):
+            if dimension != mesh.dim:
+                raise ValueError("dimension must equal the geometric dimension of the mesh")
+            self.mesh = mesh
+            self.dimension = dimension
+            self.output = output
+
+            self.S = TensorFunctionSpace(mesh, family, degree, name='S')
+            self.U = VectorFunctionSpace(mesh, family, degree, name='U')
+            dofs = self.S.mesh().num_cells() * self.S.elem.nd * dimension * dimension
+            log("Number of degrees of freedom: %d" % dofs)
+
+            self.s0 = Function(self.S, name="StressOld")
+            self.s1 = Function(self.S, name="StressNew")
+            self.u0 = Function(self.U, name="VelocityOld")
+            self.u1 = Function(self.U, name="VelocityNew")
+            # sh1/stemp/sh2 and uh1/utemp/uh2 (elastic.py:94-100) never leave the device
+
+            self.absorption_function = None
+            self.source_function = None
+            self.source_expression = None
+            self.density = None
+            self.dt = None
+            self.mu = None
+            self.l = None
+
+        if self.output:
+            with timed_region('i/o'):
+                self.u_stream = File("velocity.pvd")
+                self.s_stream = File("stress.pvd")
+
+    # -- sponge and source, as in elastic.py:127-154 ----------------------------------------------------
+    @property
+    def absorption(self):
+        return self.absorption_function
+
+    @absorption.setter
+    def absorption(self, expression):
+        self.absorption_function.interpolate(expression)
+
+    @property
+    def source(self):
+        return self.source_function
+
+    @source.setter
+    def source(self, expression):
+        self.source_function.interpolate(expression)
+
+    def write(self, u=None, s=None):
+        if self.output:
+            with timed_region('i/o'):
+                if u:
+                    self.u_stream.write(u)
+                if s:
+                    self.s_stream.write(s)
+
+
+class ExplicitElasticLF4(ElasticLF4):
+    """The explicit scheme (elastic.py:335-385) on one or more B200s."""
+
+    #: above this many (nodes x steps) the source support is found from a sample of step times, not all of them
+    SOURCE_PROBE_BUDGET = 40_000_000
+
+    def __init__(self, *args, **kwargs):
+        super(ExplicitElasticLF4, self).__init__(*args, **kwargs)
+        self._dev = None
+        self._halo = None
+        self.steps_done = 0
+        self.last_run_ms = None
+
+    # -- device setup -----------------------------------------------------------------------------------------
+    def _ensure_device(self):
+        if self._dev is None:
+            import torch
+            if not torch.cuda.is_available():
+                raise capi.SgError("no CUDA device: seigen_b200 has no CPU fallback")
+            plan = mesh_plan(self.mesh)
+            device = torch.cuda.current_device()
+            self._dev = DeviceSolver(self.mesh, self.S.degree, device=device, plan=plan)
+            if plan.nranks > 1:
+                from .halo import HaloExchanger
+                nd, d = self.S.elem.nd, self.dimension
+                self._halo = HaloExchanger(plan, nd * d * d, torch.device("cuda", device))
+                self._comm_stream = torch.cuda.ExternalStream(lib.sg_stream(self._dev.handle, 1), device=device)
+        return self._dev
+
+    def setup(self, times=None):
+        """Upload parameters (the role of elastic.py:244-255 + 369-385: nothing is assembled or inverted here,
+        the inverse mass is folded into the reference-element matrices)."""
+        log("Creating solver contexts")
+        with timed_region('solver setup'):
+            for name in ("density", "dt", "mu", "l"):
+                if getattr(self, name) is None:
+                    raise ValueError("ElasticLF4.%s must be set before run()" % name)
+            dev = self._ensure_device()
+            n_owned = dev.n_owned
+            lam, mu = self.l, self.mu
+            if np.ndim(lam) or np.ndim(mu):
+                lam = np.broadcast_to(np.asarray(lam, dtype=float), (n_owned,))
+                mu = np.broadcast_to(np.asarray(mu, dtype=float), (n_owned,))
+                lam_c, mu_c = np.ascontiguousarray(lam), np.ascontiguousarray(mu)
+                check(lib.sg_set_material(dev.handle, float(self.density), 0.0, 0.0, ptr(lam_c), ptr(mu_c)))
+            else:
+                check(lib.sg_set_material(dev.handle, float(self.density), float(lam), float(mu), None, None))
+            self._upload_absorption()
+            self._upload_source(times or [])
+
+    def _upload_absorption(self):
+        dev = self._dev
+        if self.absorption_function is None:
+            check(lib.sg_set_absorption(dev.handle, 0, None, None))
+            return
+        fs = self.absorption_function.function_space()
+        if fs.shape != ():
+            raise ValueError("absorption_function must live in a scalar DG space")
+        sig = self.absorption_function.dat.data.reshape(dev.n_owned, fs.elem.nd)
+        cells = np.flatnonzero(np.any(sig != 0.0, axis=1)).astype(np.int64)
+        if len(cells) == 0:
+            check(lib.sg_set_absorption(dev.handle, 0, None, None))
+            return
+        W = self.S.elem.absorption_tensor(fs.degree)
+        mats = np.ascontiguousarray(np.einsum("abc,eb->eac", W, sig[cells]))
+        check(lib.sg_set_absorption(dev.handle, len(cells), ptr(cells), ptr(mats)))
+
+    def _upload_source(self, times):
+        """elastic.py:285-288 re-interpolates the source over the whole stress space every step.  The values are
+        the same ones; they are computed ahead for the nodes where the expression is ever non-zero."""
+        dev = self._dev
+        if not (self.source_function is not None and self.source_expression is not None) or len(times) == 0:
+            check(lib.sg_set_source(dev.handle, 0, None, 0, None))
+            return
+        with timed_region('source term update'):
+            expr = self.source_expression
+            x = self.S.node_coords()
+            d = self.dimension
+            nnode = x.shape[0]
+            if nnode * len(times) <= self.SOURCE_PROBE_BUDGET:
+                probe = list(times)
+            else:
+                k = max(8, self.SOURCE_PROBE_BUDGET // max(nnode, 1))
+                probe = [times[i] for i in np.unique(np.linspace(0, len(times) - 1, k).astype(int))]
+            active = np.zeros(nnode, dtype=bool)
+            for t in probe:
+                v = expr.evaluate(x, t=t) if "t" in expr.user_parameters else expr.evaluate(x)
+                active |= np.any(v.reshape(nnode, -1) != 0.0, axis=1)
+            nodes = np.flatnonzero(active)
+            if len(nodes) == 0:
+                check(lib.sg_set_source(dev.handle, 0, None, 0, None))
+                return
+            xs = x[nodes]
+            amp = np.zeros((len(times), len(nodes) * d * d))
+            for n, t in enumerate(times):
+                v = expr.evaluate(xs, t=t) if "t" in expr.user_parameters else expr.evaluate(xs)
+                amp[n] = v.reshape(-1)
+            sdof = (nodes[:, None] * (d * d) + np.arange(d * d)[None, :]).reshape(-1).astype(np.int64)
+            keep = np.any(amp != 0.0, axis=0)
+            sdof, amp = np.ascontiguousarray(sdof[keep]), np.ascontiguousarray(amp[:, keep])
+            check(lib.sg_set_source(dev.handle, len(sdof), ptr(sdof), amp.shape[0], ptr(amp)))
+            if "t" in expr.user_parameters:
+                expr.t = times[-1]
+            self.source_function.interpolate(expr)
+
+    # -- state transfer ------------------------------------------------------------------------------------------
+    def _padded(self, f, shape):
+        dev = self._dev
+        nd = self.S.elem.nd
+        if dev.n_total == dev.n_owned:
+            return np.ascontiguousarray(f.dat.data)
+        out = np.zeros((dev.n_total * nd,) + shape)
+        out[:dev.n_owned * nd] = f.dat.data
+        return out
+
+    def _upload_state(self):
+        d = self.dimension
+        u = self._padded(self.u0, (d,))
+        s = self._padded(self.s0, (d, d))
+        check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+        if self._halo is not None:
+            self._exchange(capi.FIELD_U)
+            self._exchange(capi.FIELD_S)
+            check(lib.sg_compute_wait_comm(self._dev.handle))
+
+    def _download_state(self):
+        dev, d, nd = self._dev, self.dimension, self.S.elem.nd
+        if dev.n_total == dev.n_owned:
+            check(lib.sg_get_state(dev.handle, ptr(self.u1.dat.data), ptr(self.s1.dat.data)))
+        else:
+            u = np.empty((dev.n_total * nd, d))
+            s = np.empty((dev.n_total * nd, d, d))
+            check(lib.sg_get_state(dev.handle, ptr(u), ptr(s)))
+            self.u1.dat.data[...] = u[:dev.n_owned * nd]
+            self.s1.dat.data[...] = s[:dev.n_owned * nd]
+        self.u0.assign(self.u1)      # elastic.py:296
+        self.s0.assign(self.s1)      # elastic.py:304
+
+    # -- multi-GPU stage loop ------------------------------------------------------------------------------------
+    def _exchange(self, which):
+        """Send field `which` of the cut-adjacent cells, receive the neighbours' into the halo cells (comm stream)."""
+        import torch
+        dev, halo = self._dev, self._halo
+        nd, d = self.S.elem.nd, self.dimension
+        K = nd * (d if which in (capi.FIELD_U, capi.FIELD_UH) else d * d)
+        check(lib.sg_comm_wait_compute(dev.handle))
+        check(lib.sg_pack(dev.handle, which, halo.sendbuf.data_ptr(), 1))
+        with torch.cuda.stream(self._comm_stream):
+            halo.exchange(K)
+        check(lib.sg_unpack(dev.handle, which, halo.recvbuf.data_ptr(), 0, dev.plan.n_halo, 1))
+
+    _STAGE_OUTPUT = {1: capi.FIELD_UH, 2: capi.FIELD_SH, 3: capi.FIELD_U, 4: capi.FIELD_SH, 5: capi.FIELD_UH,
+                     6: capi.FIELD_S}
+
+    def _step_multi(self, nsteps, first_step):
+        dev, h = self._dev, self._dev.handle
+        dt = float(self.dt)
+        for n in range(nsteps):
+            for k in range(1, 7):
+                check(lib.sg_stage(h, k, capi.PART_BOUNDARY, dt, first_step + n))
+                self._exchange(self._STAGE_OUTPUT[k])                       # overlaps the interior launch
+                check(lib.sg_stage(h, k, capi.PART_INTERIOR, dt, first_step + n))
+                check(lib.sg_compute_wait_comm(h))
+
+    def _advance(self, nsteps, first_step):
+        if self._halo is None:
+            self._dev.step(nsteps, float(self.dt), first_step)
+        else:
+            self._step_multi(nsteps, first_step)
+
+    # -- the time loop (elastic.py:267-315) -----------------------------------------------------------------------
+    def run(self, T):
+        """Run the simulation until t = T; returns the final velocity and stress Functions."""
+        self.write(self.u1, self.s1)                      # initial condition, as elastic.py:273
+        times = step_times(T, self.dt) if self.dt else []
+        self.setup(times)
+        dev = self._dev
+        with timed_region('timestepping'):
+            self._upload_state()
+            if self.output:
+                for n in range(len(times)):
+                    self._advance(1, n)
+                    self._download_state()
+                    self.write(self.u1, self.s1)          # every step, as elastic.py:310
+            else:
+                self._advance(len(times), 0)
+                self._download_state()
+            dev.synchronize()
+        self.steps_done = len(times)
+        if self._halo is None and len(times) and not self.output:
+            self.last_run_ms = dev.last_step_ms()
+        return self.u1, self.s1
