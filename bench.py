@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Headline benchmark: DoF-time-step updates/s of the ElasticLF4 explicit update (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Workload at every N (weak scaling): BASELINE.json configs[3], the Marmousi 2D heterogeneous model at DG P2 --
+``RectangleMesh(1532*N, 484, 9192*N, 2904)`` (h = 6 m; 1 482 976 cells = 53 387 136 DoF *per GPU*; the Vp grid
+repeats with period 9192 m in x), per-cell Lame parameters mu = lambda = Vp^2/3, rho = 1, dt = 0.5*h/(2*Vp_max),
+a Ricker point source one cell row below the surface of every tile, random 1e-3 initial data.  configs[1]
+(explosive source, ~1 M DoF) is 8 MB of state -- it lives in L2 and measures launch latency, not the HBM
+roofline the metric asks for -- so it is a parity-test case (tests/), not the bench line.  The state (427 MB per
+GPU) is larger than L2 (126 MB), which is what keeps the timed iterations cold (``config.l2``).
+
+A "step" is one LF4 time step = six fused passes.  ``value`` times K steps on the device with CUDA
+events on the solver's stream (state resident in HBM); ``e2e`` times ``ElasticLF4.run(T)`` -- the call a user of
+the reference makes -- K steps per call, host (page-locked) u0/s0 copied in and u1/s1 copied out inside the timed
+region.  ``roofline`` is for the dominant kernel (pass K6, ``stage_g_kernel<AXPY>``); ``roofline_step`` for the
+whole step (64 B per DoF per step).  ``cpu_baseline`` / ``--impl reference`` time the C/OpenMP
+restatement of the reference's PyOP2 loop structure (``oracle/``; Firedrake itself cannot be installed here,
+DESIGN.md) on a bounded sample of the same workload on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dof_timestep_updates_per_sec"
+UNIT = "DoF-updates/s"
+NX, NY, LX, LY = 1532, 484, 9192.0, 2904.0
+DEGREE = 2
+VP_MAX = 5500.0
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception as exc:  # pragma: no cover
+            self.nv = None
+            self.error = repr(exc)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:  # pragma: no cover
+                    pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        self._active.set()
+        return self
+
+    def __exit__(self, *a):
+        self._active.clear()
+
+    def summary(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "error", "?")]}
+        self._stop.set()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------------
+RICKER = ("x[0] >= {x0} && x[0] <= {x1} && x[1] >= {y0} && x[1] <= {y1} ? "
+          "(-1.0 + 2*a*pow(t - t0, 2))*exp(-a*pow(t - t0, 2)) : 0.0")
+
+
+def marmousi_problem(nranks, scale=1.0):
+    """ElasticLF4 set up through the public API exactly as a reference script would (tests/explosive_source/
+    explosive_source_lf4.py:9-52), on this rank's share of the weak-scaled Marmousi mesh."""
+    from seigen_b200 import ElasticLF4, Expression, Function, RectangleMesh
+    from seigen_b200.marmousi import marmousi_lame_at
+
+    nx, ny = max(2, int(round(NX * scale))), max(2, int(round(NY * scale)))
+    mesh = RectangleMesh(nx * nranks, ny, LX * nranks, LY)
+    el = ElasticLF4.create(mesh, "DG", DEGREE, dimension=2, solver="explicit", output=False)
+    order = el.S.cell_order
+    cent = mesh.coords[mesh.cells[order]].mean(axis=1)
+    lam, mu = marmousi_lame_at(cent)
+    el.density, el.l, el.mu = 1.0, lam, mu
+    h = LX / nx
+    el.dt = 0.5 * h / (2 ** (DEGREE - 1) * VP_MAX)
+    # Ricker source (explosive_source_lf4.py:36-40) in a one-cell box below the surface of every tile
+    fpeak = 10.0
+    a = (np.pi * fpeak) ** 2
+    boxes = []
+    for r in range(nranks):
+        xc = LX * (r + 0.5)
+        boxes.append(RICKER.format(x0=xc - 0.5 * h, x1=xc + 0.5 * h, y0=LY - 1.5 * h, y1=LY - 0.5 * h))
+    src = " + ".join("(" + b + ")" for b in boxes)
+    el.source_expression = Expression(((src, "0.0"), ("0.0", src)), a=a, t0=0.1, t=0.0)
+    el.source_function = Function(el.S)
+    el.source = el.source_expression
+    rng = np.random.default_rng(1234 + el.S.plan.rank)
+    el.u0.dat.data[...] = 1e-3 * rng.standard_normal(el.u0.dat.data.shape)
+    el.s0.dat.data[...] = 1e-3 * rng.standard_normal(el.s0.dat.data.shape)
+    name = f"marmousi_2d_p{DEGREE}_{nx}x{ny}_per_gpu"
+    return el, name
+
+
+def sample_problem():
+    """Bounded CPU sample of the same workload: the Marmousi grid at its native h = 24 m (seigen/marmousi.py:18-21),
+    P2 -- 92 686 cells, 3 336 696 DoF, same materials rule, same dt rule."""
+    from oracle.c_oracle import COracle
+    from oracle.elastic_oracle import ElasticOracle
+    from seigen_b200.marmousi import marmousi_lame
+    from seigen_b200.mesh import RectangleMesh
+
+    mesh = RectangleMesh(383, 121, LX, LY)
+    orc = ElasticOracle(mesh.coords, mesh.cells, DEGREE)
+    lam, mu = marmousi_lame(mesh)
+    orc.l, orc.mu, orc.density = lam, mu, 1.0
+    orc.dt = 0.5 * 24.0 / (2 ** (DEGREE - 1) * VP_MAX)
+    co = COracle(orc)
+    E, nd = orc.E, orc.nd
+    rng = np.random.default_rng(7)
+    u = 1e-3 * rng.standard_normal((E, nd, 2))
+    s = 1e-3 * rng.standard_normal((E, nd, 2, 2))
+    ndof = E * nd * 6
+    return co, u, s, orc.dt, ndof, f"Marmousi 2D P{DEGREE} at h=24 m: {E} cells, {ndof} DoF"
+
+
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    --set full capture of this workload (profiles/dominant_kernel_traffic.json), or None if not captured yet."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))["bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def time_cpu(co, u, s, dt, steps, warmup):
+    for _ in range(warmup):
+        co.step_inplace(u, s, None, dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.step_inplace(u, s, None, dt)
+    return time.perf_counter() - t0
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    co, u, s, dt, ndof, sample = sample_problem()
+    # each bench step = one LF4 time step of the sample; cap so that the whole run stays within a few minutes
+    t_probe = time_cpu(co, u, s, dt, 1, 1)
+    steps = max(1, min(args.steps, int(120.0 / max(t_probe, 1e-6))))
+    warm = max(1, min(args.warmup, int(30.0 / max(t_probe, 1e-6))))
+    wall = time_cpu(co, u, s, dt, steps, warm)
+    val = ndof * steps / wall
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"marmousi_2d_p{DEGREE}", "sample": sample, "degree": DEGREE,
+                      "note": "Firedrake/PyOP2 cannot be installed here; this is the C/OpenMP restatement of the "
+                              "reference's PyOP2 loop structure (oracle/elastic_c.c), all host threads"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": co.threads, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (seigen_b200 has no CPU fallback; use --impl reference for the CPU arm)")
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    from seigen_b200 import capi
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t_setup = time.perf_counter()
+    el, wname = marmousi_problem(world, args.scale)
+    K, W = args.steps, max(3, args.warmup)
+    dt = float(el.dt)
+    T = (K + 0.5) * dt
+    # first run(): builds the rank plan, uploads geometry/material/source table, captures the graph (untimed)
+    el.run((W + 0.5) * dt)
+    dev = el._dev
+    nd, d = el.S.elem.nd, 2
+    ndof_local = dev.n_owned * nd * (d + d * d)
+    ndof = sum_over_ranks(ndof_local)
+    t_setup = time.perf_counter() - t_setup
+    sampler = ClockSampler(local)
+
+    # ---- value: K steps, state resident in HBM, CUDA events on the solver's stream, max over ranks -----------
+    el.setup([dt * (i + 1) for i in range(K)])
+    el._upload_state()
+    el._advance(W, 0)
+    barrier()
+    with sampler:
+        el._advance(K, 0)
+        barrier()
+    ms_local = dev.last_step_ms()
+    ms = max_over_ranks(ms_local)
+    value = ndof * K / (ms * 1e-3)
+    nsrc_kernels = 4 if el.source_function is not None else 0
+    launches = K * (6 + nsrc_kernels) if world == 1 else K * (12 + 12 + 3)   # per step: see DESIGN.md
+
+    # ---- per-pass timing of the six kernels (roofline of the dominant one) ----------------------------------
+    reps = max(10, min(K, 50))
+    stage_ms = [dev.time_stage(k, dt * 1e-3, reps) for k in range(1, 7)]
+    E = dev.n_owned
+    cell_doubles = {1: 6, 2: 6, 3: 10, 4: 6, 5: 6, 6: 14}       # field doubles per node per pass
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    stages = []
+    for k in range(1, 7):
+        b = cell_doubles[k] * nd * 8.0 * E
+        stages.append({"pass": f"K{k}", "ms": stage_ms[k - 1], "alg_bytes": b, "gbs": b / stage_ms[k - 1] / 1e6})
+    dom = stages[5]
+    roofline = {"kernel": "stage_g_kernel<2,2,AXPY> (pass K6: s1 = s0 + dt*sh1 + dt^3/24*(Ds(utemp)+src))",
+                "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
+                "traffic": profiled_traffic(), "peak_source": peak_src,
+                "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"]}
+    step_gbs = 64.0 * ndof_local * K / (ms_local * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                     "alg_bytes_per_dof_step": 64, "note": "per GPU, whole step = 6 passes"}
+
+    # ---- e2e: ElasticLF4.run(T), host page-locked state in and out inside the timed region -------------------
+    el.run(T)                                   # warm: source table for these K steps, graph
+    walls = []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        with sampler:
+            el.run(T)
+            barrier()
+        walls.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_wall = float(np.mean(walls))
+    state_bytes = sum_over_ranks(el.u0.dat.data.nbytes + el.s0.dat.data.nbytes)
+    e2e = {"value": ndof * K / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": state_bytes / K,
+           "d2h_bytes_per_step": state_bytes / K, "call": f"ElasticLF4.run(T) with T = {K} steps per call",
+           "h2d_bytes_per_call": state_bytes, "d2h_bytes_per_call": state_bytes, "wall_s_per_call": e2e_wall}
+    clocks = sampler.summary()
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        co, u, s, cdt, cndof, sample = sample_problem()
+        t1 = time_cpu(co, u, s, cdt, 1, 1)
+        csteps = max(2, min(60, int(15.0 / max(t1, 1e-6))))
+        cw = time_cpu(co, u, s, cdt, csteps, 0)
+        cpu = {"value": cndof * csteps / cw, "unit": UNIT, "cores": co.threads, "kind": "port",
+               "sample": f"{sample}, {csteps} steps"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": wname, "degree": DEGREE, "dim": 2, "cells_per_gpu": int(E),
+                          "dof_per_gpu": int(ndof_local), "dof_total": int(ndof), "dt": dt,
+                          "material": "per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1",
+                          "source": "Ricker, one cell box per tile", "sponge": "none",
+                          "l2": "state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)" % (8e-6 * ndof_local),
+                          "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass",
+                          "setup_s": t_setup},
+               "roofline": roofline, "roofline_step": roofline_step, "stages": stages,
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=env_int("WORLD_SIZE", 1))
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="mesh resolution factor (development aid; 1 = headline)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,10 @@ int sg_synchronize(sg_solver* h);
 /* Device time in milliseconds between the start and the end of the last sg_step call (CUDA events on the
  * solver's stream); synchronises. */
 int sg_last_step_ms(sg_solver* h, double* ms);
+/* Records the start (which = 0) / end (which = 1) event of that interval on the compute stream by hand: for
+ * drivers that advance stage by stage with sg_stage (the role of PyOP2's timed_region('timestepping'),
+ * elastic.py:278). */
+int sg_mark(sg_solver* h, int which);
 
 /* One of the six fused passes (K1 uh1, K2 stemp, K3 u1, K4 sh1, K5 utemp, K6 s1), on all cells or on
  * the boundary / interior part.  Used by per-stage parity tests and by the multi-GPU driver, which exchanges

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["lib", "load", "SgError", "MeshDesc", "LIB_PATH", "check",
+__all__ = ["lib", "load", "SgError", "MeshDesc", "LIB_PATH", "check", "pinned_zeros",
            "FIELD_U", "FIELD_S", "FIELD_UH", "FIELD_SH", "PART_ALL", "PART_BOUNDARY", "PART_INTERIOR"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libseigen_b200.so")
@@ -55,6 +55,7 @@ _SIGNATURES = {
     "sg_step": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int64]),
     "sg_synchronize": (C.c_int, [_P]),
     "sg_last_step_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "sg_mark": (C.c_int, [_P, C.c_int]),
     "sg_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int64]),
     "sg_time_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "sg_set_halo_plan": (C.c_int, [_P, C.c_int64, _P]),
@@ -106,6 +107,24 @@ def check(rc: int):
     if rc != 0:
         msg = load().sg_last_error()
         raise SgError(f"seigen_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def pinned_zeros(shape):
+    """Zero-filled float64 array in page-locked host memory (``sg_host_alloc``), freed with the array.  The state
+    Functions of ``ElasticLF4`` live in such arrays so that ``sg_set_state`` / ``sg_get_state`` run at PCIe speed."""
+    import weakref
+    n = int(np.prod(shape, dtype=np.int64))
+    if n == 0:
+        return np.zeros(shape)
+    l = load()
+    p = l.sg_host_alloc(n * 8)
+    if not p:
+        raise SgError("sg_host_alloc failed: " + (l.sg_last_error() or b"?").decode())
+    buf = (C.c_double * n).from_address(p)
+    a = np.ctypeslib.as_array(buf).reshape(shape)
+    weakref.finalize(buf, l.sg_host_free, C.c_void_p(p))
+    a[...] = 0.0
+    return a
 
 
 def ptr(a):

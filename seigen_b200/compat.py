@@ -113,8 +113,10 @@ class FunctionSpace:
 
     def node_coords(self):
         """(n_owned*nd, d) physical coordinates of the owned nodes, local order."""
-        x = self.mesh_.node_coords(self.elem)[self.cell_order]
-        return x.reshape(-1, self.mesh_.dim)
+        m = self.mesh_
+        v = m.coords[m.cells[self.cell_order]]                                  # (n_owned, d+1, d)
+        lam = self.elem.lattice.astype(np.float64) / self.elem.degree          # (nd, d+1) barycentric
+        return np.einsum("av,evk->eak", lam, v).reshape(-1, m.dim)
 
 
 def VectorFunctionSpace(mesh, family, degree, name=None, dim=None):
@@ -135,13 +137,13 @@ class _Dat:
 
 
 class Function:
-    def __init__(self, function_space, val=None, name=None):
+    def __init__(self, function_space, val=None, name=None, alloc=np.zeros):
         if isinstance(function_space, Function):
             val = function_space.dat.data
             function_space = function_space.function_space()
         self._fs = function_space
         self._name = name
-        data = np.zeros((function_space.node_count,) + function_space.shape)
+        data = alloc((function_space.node_count,) + function_space.shape)
         if val is not None:
             data[...] = np.asarray(val).reshape(data.shape)
         self.dat = _Dat(data)

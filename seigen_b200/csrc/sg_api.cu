@@ -675,6 +675,13 @@ int sg_synchronize(sg_solver* h) {
   return SG_OK;
 }
 
+int sg_mark(sg_solver* h, int which) {
+  if (!h || (which != 0 && which != 1)) return fail(SG_EINVAL, "sg_mark: bad arguments");
+  SG_CUDA(cudaSetDevice(h->device));
+  SG_CUDA(cudaEventRecord(which ? h->ev1 : h->ev0, h->stream));
+  return SG_OK;
+}
+
 int sg_last_step_ms(sg_solver* h, double* ms) {
   if (!h || !ms) return fail(SG_EINVAL, "sg_last_step_ms: null argument");
   SG_CUDA(cudaSetDevice(h->device));

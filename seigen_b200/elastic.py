@@ -64,10 +64,11 @@ class ElasticLF4(object):
             dofs = self.S.mesh().num_cells() * self.S.elem.nd * dimension * dimension
             log("Number of degrees of freedom: %d" % dofs)
 
-            self.s0 = Function(self.S, name="StressOld")
-            self.s1 = Function(self.S, name="StressNew")
-            self.u0 = Function(self.U, name="VelocityOld")
-            self.u1 = Function(self.U, name="VelocityNew")
+            alloc = self._state_alloc()
+            self.s0 = Function(self.S, name="StressOld", alloc=alloc)
+            self.s1 = Function(self.S, name="StressNew", alloc=alloc)
+            self.u0 = Function(self.U, name="VelocityOld", alloc=alloc)
+            self.u1 = Function(self.U, name="VelocityNew", alloc=alloc)
             # sh1/stemp/sh2 and uh1/utemp/uh2 (elastic.py:94-100) never leave the device
 
             self.absorption_function = None
@@ -82,6 +83,19 @@ class ElasticLF4(object):
             with timed_region('i/o'):
                 self.u_stream = File("velocity.pvd")
                 self.s_stream = File("stress.pvd")
+
+    @staticmethod
+    def _state_alloc():
+        """Allocator of the host arrays behind u0/u1/s0/s1: page-locked when a CUDA device is present, so that the
+        state crosses PCIe at full speed in run(); plain NumPy otherwise (host-only use: building initial data)."""
+        try:
+            import torch
+            if torch.cuda.is_available():
+                capi.load()
+                return capi.pinned_zeros
+        except capi.SgError:
+            pass
+        return np.zeros
 
     # -- sponge and source, as in elastic.py:127-154 ----------------------------------------------------
     @property
@@ -182,9 +196,15 @@ class ExplicitElasticLF4(ElasticLF4):
         dev = self._dev
         if not (self.source_function is not None and self.source_expression is not None) or len(times) == 0:
             check(lib.sg_set_source(dev.handle, 0, None, 0, None))
+            self._source_key = None
             return
+        expr = self.source_expression
+        key = (id(expr), expr.code_key(), tuple(sorted((k, v) for k, v in expr.user_parameters.items() if k != "t")),
+               len(times), times[0], times[-1])
+        if key == getattr(self, "_source_key", None):
+            return                       # same expression over the same step times: the device table is current
+        self._source_key = None
         with timed_region('source term update'):
-            expr = self.source_expression
             x = self.S.node_coords()
             d = self.dimension
             nnode = x.shape[0]
@@ -212,7 +232,10 @@ class ExplicitElasticLF4(ElasticLF4):
             check(lib.sg_set_source(dev.handle, len(sdof), ptr(sdof), amp.shape[0], ptr(amp)))
             if "t" in expr.user_parameters:
                 expr.t = times[-1]
-            self.source_function.interpolate(expr)
+            # what elastic.py:288 leaves in source_function after the last step
+            self.source_function.dat.data[...] = 0.0
+            self.source_function.dat.data.reshape(-1)[sdof] = amp[-1]
+            self._source_key = key
 
     # -- state transfer ------------------------------------------------------------------------------------------
     def _padded(self, f, shape):
@@ -244,8 +267,8 @@ class ExplicitElasticLF4(ElasticLF4):
             check(lib.sg_get_state(dev.handle, ptr(u), ptr(s)))
             self.u1.dat.data[...] = u[:dev.n_owned * nd]
             self.s1.dat.data[...] = s[:dev.n_owned * nd]
-        self.u0.assign(self.u1)      # elastic.py:296
-        self.s0.assign(self.s1)      # elastic.py:304
+        np.copyto(self.u0.dat.data, self.u1.dat.data)      # elastic.py:296
+        np.copyto(self.s0.dat.data, self.s1.dat.data)      # elastic.py:304
 
     # -- multi-GPU stage loop ------------------------------------------------------------------------------------
     def _exchange(self, which):
@@ -266,12 +289,14 @@ class ExplicitElasticLF4(ElasticLF4):
     def _step_multi(self, nsteps, first_step):
         dev, h = self._dev, self._dev.handle
         dt = float(self.dt)
+        check(lib.sg_mark(h, 0))
         for n in range(nsteps):
             for k in range(1, 7):
                 check(lib.sg_stage(h, k, capi.PART_BOUNDARY, dt, first_step + n))
                 self._exchange(self._STAGE_OUTPUT[k])                       # overlaps the interior launch
                 check(lib.sg_stage(h, k, capi.PART_INTERIOR, dt, first_step + n))
                 check(lib.sg_compute_wait_comm(h))
+        check(lib.sg_mark(h, 1))
 
     def _advance(self, nsteps, first_step):
         if self._halo is None:
@@ -298,6 +323,6 @@ class ExplicitElasticLF4(ElasticLF4):
                 self._download_state()
             dev.synchronize()
         self.steps_done = len(times)
-        if self._halo is None and len(times) and not self.output:
+        if len(times) and not self.output:
             self.last_run_ms = dev.last_step_ms()
         return self.u1, self.s1

@@ -226,6 +226,12 @@ class Expression:
     def value_shape(self):
         return self._shape
 
+    def code_key(self):
+        """Hashable form of the source text (cache key for precomputed tables)."""
+        def flat(c):
+            return tuple(flat(k) for k in c) if isinstance(c, (tuple, list)) else str(c)
+        return flat(self.code)
+
     @property
     def user_parameters(self):
         return dict(self._params)

@@ -127,20 +127,32 @@ class RankPlan:
 
 
 def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> RankPlan:
-    topo: Topology = mesh.topology
-    E, nf = topo.nbr.shape
+    """Local numbering of rank ``rank``.  With more than one rank only the sub-mesh made of the owned cells and
+    the cells that share a vertex with them (a superset of the facet neighbours) gets its adjacency built, so
+    the cost per rank follows the rank's share of the mesh, not the global mesh."""
     part = np.asarray(part)
-    owned_mask = part == rank
-    owned = np.flatnonzero(owned_mask)
+    E = mesh.num_cells()
+    if nranks > 1:
+        vflag = np.zeros(mesh.num_vertices(), dtype=bool)
+        vflag[mesh.cells[part == rank].reshape(-1)] = True
+        sub = np.flatnonzero(vflag[mesh.cells].any(axis=1))          # ascending global ids
+        from .mesh import build_topology
+        topo = build_topology(mesh.coords, mesh.cells[sub])
+        cent = mesh.coords[mesh.cells[sub]].mean(axis=1)
+    else:
+        sub = np.arange(E)
+        topo = mesh.topology
+        cent = mesh.cell_centroids()
+    spart = part[sub]
+    nf = topo.nbr.shape[1]
+    owned = np.flatnonzero(spart == rank)                             # sub-mesh indices from here on
     if len(owned) == 0:
         raise ValueError(f"rank {rank} owns no cells")
-    nb = topo.nbr[owned]                                          # global neighbour ids
-    nb_part = part[nb]
-    remote = nb_part != rank                                      # (n_owned, nf); exterior facets point to self
+    nb = topo.nbr[owned]
+    remote = spart[nb] != rank                                        # exterior facets point to self
     is_bnd = remote.any(axis=1)
 
-    cent = mesh.cell_centroids()
-    key = hilbert_key(cent)                                       # one global curve: consistent across ranks
+    key = hilbert_key(cent)
     o_b = owned[is_bnd]
     o_i = owned[~is_bnd]
     o_b = o_b[np.argsort(key[o_b], kind="stable")]
@@ -148,8 +160,9 @@ def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> Ran
     owned_sorted = np.concatenate([o_b, o_i])
 
     # halo: remote cells across a facet of an owned cell, grouped by owner, ascending global id inside a group
+    # (sub-mesh indices ascend with global ids, so every rank derives the same order)
     halo_ids = np.unique(nb[remote])
-    halo_owner = part[halo_ids]
+    halo_owner = spart[halo_ids]
     order = np.lexsort((halo_ids, halo_owner))
     halo_ids, halo_owner = halo_ids[order], halo_owner[order]
     recv = {}
@@ -157,11 +170,11 @@ def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> Ran
         sel = np.flatnonzero(halo_owner == q)
         recv[int(q)] = (int(sel[0]), int(len(sel)))
 
-    l2g = np.concatenate([owned_sorted, halo_ids]).astype(np.int64)
-    g2l = np.full(E, -1, dtype=np.int64)
-    g2l[l2g] = np.arange(len(l2g))
+    l2s = np.concatenate([owned_sorted, halo_ids]).astype(np.int64)
+    s2l = np.full(len(sub), -1, dtype=np.int64)
+    s2l[l2s] = np.arange(len(l2s))
 
-    nbr_local = g2l[topo.nbr[owned_sorted]]
+    nbr_local = s2l[topo.nbr[owned_sorted]]
     assert (nbr_local >= 0).all()
     code = topo.code[owned_sorted].copy()
     jinv = np.ascontiguousarray(topo.jinv[owned_sorted])
@@ -169,18 +182,17 @@ def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> Ran
     # send lists: my cells that peer q sees across its facets = my cut-adjacent cells with a neighbour owned by q,
     # in ascending global id (the order q's halo group uses)
     send, send_offsets, chunks, off = {}, {}, [], 0
-    nb_b = topo.nbr[o_b]
-    pb = part[nb_b]
+    pb = spart[topo.nbr[o_b]]
     for q in sorted(recv):
         mine = np.unique(o_b[(pb == q).any(axis=1)])
-        loc = g2l[mine]
+        loc = s2l[mine]
         send[q] = loc
         send_offsets[q] = (off, len(loc))
         chunks.append(loc)
         off += len(loc)
     send_cells = np.concatenate(chunks).astype(np.int64) if chunks else np.zeros(0, dtype=np.int64)
 
-    return RankPlan(rank=rank, nranks=nranks, local_to_global=l2g, n_owned=len(owned_sorted),
+    return RankPlan(rank=rank, nranks=nranks, local_to_global=sub[l2s].astype(np.int64), n_owned=len(owned_sorted),
                     n_boundary=len(o_b), nbr=np.ascontiguousarray(nbr_local.astype(np.int32)),
                     code=np.ascontiguousarray(code.astype(np.uint8)), jinv=jinv, recv=recv, send=send,
                     send_cells=send_cells, send_offsets=send_offsets)

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["load_vp_grid", "marmousi_vp", "marmousi_lame", "LX", "LY"]
+__all__ = ["load_vp_grid", "marmousi_vp", "marmousi_lame", "marmousi_lame_at", "LX", "LY"]
 
 LX, LY = 9192.0, 2904.0
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "marmousi_vp.npz")
@@ -32,8 +32,13 @@ def marmousi_vp(points):
     return data[i, -j]
 
 
-def marmousi_lame(mesh):
-    """Per-cell (lambda, mu) in the mesh's global cell order, Poisson solid with rho = 1 (P speed = Vp)."""
-    vp = marmousi_vp(mesh.cell_centroids())
+def marmousi_lame_at(points):
+    """(lambda, mu) at points (n, 2): Poisson solid with rho = 1, so that the P speed is Vp."""
+    vp = marmousi_vp(points)
     mu = vp * vp / 3.0
     return mu.copy(), mu
+
+
+def marmousi_lame(mesh):
+    """Per-cell (lambda, mu) in the mesh's global cell order, sampled at the cell centroids."""
+    return marmousi_lame_at(mesh.cell_centroids())
