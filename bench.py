@@ -277,7 +277,10 @@ def run_gpu(args):
     ms = max_over_ranks(ms_local)
     value = ndof * K / (ms * 1e-3)
     nsrc_kernels = 4 if el.source_function is not None else 0
-    launches = K * (6 + nsrc_kernels) if world == 1 else K * (12 + 12 + 3)   # per step: see DESIGN.md
+    if world == 1:
+        launches = K * (6 + nsrc_kernels)                      # 6 passes (+3 source adds +1 step counter)
+    else:                                                      # per pass: boundary, interior, push, signal, wait
+        launches = K * (6 * 5 + (7 if nsrc_kernels else 0))
 
     # ---- per-pass timing of the six kernels (roofline of the dominant one) ----------------------------------
     reps = max(10, min(K, 50))
@@ -306,6 +309,9 @@ def run_gpu(args):
 
     # ---- e2e: ElasticLF4.run(T), host page-locked state in and out inside the timed region -------------------
     el.run(T)                                   # warm: source table for these K steps, graph
+    if os.environ.get("SG_BENCH_DEBUG"):
+        from seigen_b200 import get_timers
+        get_timers(reset=True)
     walls = []
     for _ in range(2):
         barrier()
@@ -315,6 +321,9 @@ def run_gpu(args):
             barrier()
         walls.append(max_over_ranks(time.perf_counter() - t0))
     e2e_wall = float(np.mean(walls))
+    if os.environ.get("SG_BENCH_DEBUG") and rank == 0:
+        from seigen_b200 import get_timers
+        print("timers:", {k: round(v, 4) for k, v in get_timers().items()}, "walls:", walls, file=sys.stderr)
     state_bytes = sum_over_ranks(el.u0.dat.data.nbytes + el.s0.dat.data.nbytes)
     e2e = {"value": ndof * K / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": state_bytes / K,
            "d2h_bytes_per_step": state_bytes / K, "call": f"ElasticLF4.run(T) with T = {K} steps per call",
@@ -340,12 +349,13 @@ def run_gpu(args):
                           "material": "per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1",
                           "source": "Ricker, one cell box per tile", "sponge": "none",
                           "l2": "state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)" % (8e-6 * ndof_local),
-                          "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass",
+                          "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass, exchange={el.halo_mode}",
                           "setup_s": t_setup},
                "roofline": roofline, "roofline_step": roofline_step, "stages": stages,
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -89,10 +89,11 @@ int sg_set_absorption(sg_solver* h, int64_t n, const int64_t* cell, const double
  * nsrc = 0 clears. */
 int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nsteps, const double* amp);
 
-/* u0.assign / s0.assign (tests/explosive_source/explosive_source_lf4.py:48-52); arrays are [n_total*nd][d] and
- * [n_total*nd][d][d].  Either pointer may be NULL (field left unchanged). */
+/* u0.assign / s0.assign (tests/explosive_source/explosive_source_lf4.py:48-52); arrays are [n_owned*nd][d] and
+ * [n_owned*nd][d][d] (owned cells; halo cells are filled by the halo exchange).  Either pointer may be NULL (field
+ * left unchanged). */
 int sg_set_state(sg_solver* h, const double* u, const double* s);
-/* u1.dat.data / s1.dat.data after run (elastic.py:315).  Synchronises with all queued work. */
+/* u1.dat.data / s1.dat.data after run (elastic.py:315), owned cells.  Synchronises with all queued work. */
 int sg_get_state(sg_solver* h, double* u, double* s);
 int sg_get_field(sg_solver* h, int which, double* out);
 
@@ -131,6 +132,32 @@ int sg_comm_wait_compute(sg_solver* h);   /* comm stream waits for everything qu
 int sg_compute_wait_comm(sg_solver* h);   /* compute stream waits for everything queued on comm */
 void* sg_stream(sg_solver* h, int comm);  /* cudaStream_t, for torch.cuda.ExternalStream */
 void* sg_field_ptr(sg_solver* h, int which);
+
+/* Peer-memory halo exchange (one process per GPU on one NVSwitch domain).  Instead of packing into a buffer
+ * that a library sends, each rank writes the rows of its cut-adjacent cells straight into the halo tiles of the
+ * neighbouring ranks' fields through CUDA-IPC mappings (NVLink stores), then publishes an epoch flag in the
+ * neighbour's memory; the consumer spins on its own flag.  With peers connected, sg_step replays ONE CUDA graph per
+ * time step that contains all six passes and all six exchanges (boundary tiles -> push/signal/wait on the comm
+ * stream, overlapped with the interior tiles) -- no host work and no library call inside a step.
+ *   sg_ipc_export    5 handles of SG_IPC_HANDLE_BYTES bytes: u, s, uh, sh, control words
+ *   sg_peer_connect  the handles of every neighbouring rank + where my cells land in its fields
+ *   sg_exchange      one immediate exchange of field `which` on the compute stream (after sg_set_state)
+ *   sg_peer_error    synchronises; *err != 0 if a wait timed out (a peer never published its rows)
+ * Every rank must issue the same sequence of exchanges.  The halo cells of a field are written by exchanges only
+ * (sg_set_state ignores the halo part of its arguments). */
+#define SG_IPC_HANDLE_BYTES 64
+typedef struct sg_peer_desc {
+  int32_t rank;               /* the neighbour (informational) */
+  int32_t flag_slot;          /* my index among that neighbour's peers: the control word I publish into */
+  int64_t send_offset;        /* my cells for this neighbour: send_cells[send_offset, send_offset + send_count) */
+  int64_t send_count;
+  int64_t remote_first_cell;  /* device cell index (tile-padded) of the first of them in the neighbour's fields */
+  unsigned char handles[5][SG_IPC_HANDLE_BYTES];
+} sg_peer_desc;
+int sg_ipc_export(sg_solver* h, unsigned char* out);
+int sg_peer_connect(sg_solver* h, int32_t npeers, const sg_peer_desc* peers);
+int sg_exchange(sg_solver* h, int which);
+int sg_peer_error(sg_solver* h, int64_t* err);
 
 /* Sizes, so that a binding can allocate: nd nodes per cell, tile (cells per device tile). */
 int sg_nodes_per_cell(int dim, int degree);

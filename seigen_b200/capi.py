@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["lib", "load", "SgError", "MeshDesc", "LIB_PATH", "check", "pinned_zeros",
+__all__ = ["lib", "load", "SgError", "MeshDesc", "LIB_PATH", "check", "pinned_zeros", "PeerDesc",
            "FIELD_U", "FIELD_S", "FIELD_UH", "FIELD_SH", "PART_ALL", "PART_BOUNDARY", "PART_INTERIOR"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libseigen_b200.so")
@@ -40,6 +40,17 @@ class MeshDesc(C.Structure):
     ]
 
 
+class PeerDesc(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32),
+        ("flag_slot", C.c_int32),
+        ("send_offset", C.c_int64),
+        ("send_count", C.c_int64),
+        ("remote_first_cell", C.c_int64),
+        ("handles", (C.c_ubyte * 64) * 5),
+    ]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "sg_last_error": (C.c_char_p, []),
@@ -63,6 +74,10 @@ _SIGNATURES = {
     "sg_unpack": (C.c_int, [_P, C.c_int, _P, C.c_int64, C.c_int64, C.c_int]),
     "sg_comm_wait_compute": (C.c_int, [_P]),
     "sg_compute_wait_comm": (C.c_int, [_P]),
+    "sg_ipc_export": (C.c_int, [_P, _P]),
+    "sg_peer_connect": (C.c_int, [_P, C.c_int32, C.POINTER(PeerDesc)]),
+    "sg_exchange": (C.c_int, [_P, C.c_int]),
+    "sg_peer_error": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sg_stream": (_P, [_P, C.c_int]),
     "sg_field_ptr": (_P, [_P, C.c_int]),
     "sg_nodes_per_cell": (C.c_int, [C.c_int, C.c_int]),

@@ -128,12 +128,37 @@ def TensorFunctionSpace(mesh, family, degree, name=None, shape=None):
 
 
 class _Dat:
+    """``Function.dat``: ``data`` is the NumPy array of the owned nodes.  ``defer_copy_from(other)`` makes this Dat
+    a lazy copy of another one (the ``u0.assign(u1)`` at the end of a time step, elastic.py:296): the bytes are
+    copied when ``data`` is next looked at, not before."""
+
     def __init__(self, data):
-        self.data = data
+        self._data = data
+        self._lazy_from = None
+
+    @property
+    def data(self):
+        src = self._lazy_from
+        if src is not None:
+            self._lazy_from = None
+            np.copyto(self._data, src.data)
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._lazy_from = None
+        self._data = value
 
     @property
     def data_ro(self):
         return self.data
+
+    def defer_copy_from(self, other):
+        self._lazy_from = other if other is not self else None
+
+    def current_source(self):
+        """The Dat whose array currently holds this Dat's values (itself unless a deferred copy is pending)."""
+        return self._lazy_from if self._lazy_from is not None else self
 
 
 class Function:

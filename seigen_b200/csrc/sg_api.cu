@@ -95,6 +95,7 @@ template <class T> struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaError_t alloc(size_t count) {
+    if (p && count == n) return cudaSuccess;   // same size: keep the buffer (pointers baked into CUDA graphs stay valid)
     release();
     n = count;
     if (count == 0) return cudaSuccess;
@@ -127,7 +128,16 @@ struct sg_solver {
   double density = 1.0, lam_c = 0.0, mu_c = 0.0;
   cudaStream_t stream = nullptr, comm = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
-  // CUDA graph of one time step (single-GPU path)
+  // peer-memory halo exchange (CUDA IPC): see sg_peer_connect
+  int npeers = 0;
+  std::vector<void*> ipc_opened;
+  DevBuf<unsigned long long> ctl;            // flags + epoch counters (sg::SG_CTL_*)
+  DevBuf<int64_t> send_dst;                  // [nsend] device cell index in the destination rank's fields
+  DevBuf<int32_t> send_peer;                 // [nsend] index into the peer tables
+  DevBuf<double*> rfield;                    // [4][npeers] peers' u, s, uh, sh
+  DevBuf<unsigned long long*> rflag;         // [npeers] my flag slot in each peer's ctl
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // CUDA graph of one time step
   cudaGraphExec_t graph = nullptr;
   double graph_dt = 0.0;
   uint64_t config_version = 0, graph_version = ~0ull;
@@ -231,16 +241,56 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
   return SG_OK;
 }
 
-int relayout(sg_solver* h, double* dev, double* host_order, int ncomp, bool to_device, cudaStream_t st) {
-  const int64_t total = h->n_total * h->nd * ncomp;
+int relayout(sg_solver* h, double* dev, double* host_order, int ncomp, bool to_device, cudaStream_t st,
+             int64_t ncell) {
+  const int64_t total = ncell * h->nd * ncomp;
   if (total == 0) return SG_OK;
   if (to_device)
-    sg::relayout_kernel<true><<<grid_for(total), 256, 0, st>>>(dev, host_order, h->n_total, h->n_owned,
+    sg::relayout_kernel<true><<<grid_for(total), 256, 0, st>>>(dev, host_order, ncell, h->n_owned,
                                                                h->n_owned_pad, h->nd, ncomp, h->tile);
   else
-    sg::relayout_kernel<false><<<grid_for(total), 256, 0, st>>>(dev, host_order, h->n_total, h->n_owned,
+    sg::relayout_kernel<false><<<grid_for(total), 256, 0, st>>>(dev, host_order, ncell, h->n_owned,
                                                                 h->n_owned_pad, h->nd, ncomp, h->tile);
   SG_CUDA(cudaGetLastError());
+  return SG_OK;
+}
+
+DevBuf<double>* field_buf(sg_solver* h, int which);
+int field_ncomp(sg_solver* h, int which);
+
+// push my cut-adjacent cells of field `which` into the peers' halo tiles, publish, then wait for the peers' rows
+int enqueue_exchange(sg_solver* h, int which, cudaStream_t st) {
+  if (h->npeers == 0) return SG_OK;
+  const int K = field_ncomp(h, which) * h->nd;
+  sg::push_kernel<<<grid_for(h->nsend * K), 256, 0, st>>>(field_buf(h, which)->p, h->send_cells.p, h->send_dst.p,
+                                                          h->send_peer.p, h->rfield.p + (size_t)which * h->npeers,
+                                                          h->nsend, K, h->tile);
+  SG_CUDA(cudaGetLastError());
+  sg::signal_kernel<<<1, 32, 0, st>>>(h->ctl.p, h->rflag.p, h->npeers);
+  SG_CUDA(cudaGetLastError());
+  sg::wait_kernel<<<1, 32, 0, st>>>(h->ctl.p, h->npeers, (long long)40e9);
+  SG_CUDA(cudaGetLastError());
+  return SG_OK;
+}
+
+const int STAGE_OUTPUT[7] = {-1, SG_FIELD_UH, SG_FIELD_SH, SG_FIELD_U, SG_FIELD_SH, SG_FIELD_UH, SG_FIELD_S};
+
+// One time step on a rank with peers: per pass, cut-adjacent tiles first, then their rows travel on the comm
+// stream (push -> signal -> wait) while the interior tiles are computed on the compute stream.
+int enqueue_step_peers(sg_solver* h, double dt) {
+  cudaStream_t st = h->stream, cm = h->comm;
+  for (int k = 1; k <= 6; ++k) {
+    int rc = launch_stage(h, k, SG_PART_BOUNDARY, dt, st);
+    if (rc) return rc;
+    SG_CUDA(cudaEventRecord(h->ev_fork, st));
+    SG_CUDA(cudaStreamWaitEvent(cm, h->ev_fork, 0));
+    rc = enqueue_exchange(h, STAGE_OUTPUT[k], cm);
+    if (rc) return rc;
+    rc = launch_stage(h, k, SG_PART_INTERIOR, dt, st);
+    if (rc) return rc;
+    SG_CUDA(cudaEventRecord(h->ev_join, cm));
+    SG_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
   return SG_OK;
 }
 
@@ -329,6 +379,10 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   SG_CUDA_H(cudaEventCreate(&h->ev0));
   SG_CUDA_H(cudaEventCreate(&h->ev1));
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
+  SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  SG_CUDA_H(h->ctl.alloc(sg::SG_CTL_WORDS));
+  SG_CUDA_H(cudaMemsetAsync(h->ctl.p, 0, sg::SG_CTL_WORDS * 8, h->stream));
 
   const size_t nU = (size_t)h->n_dev * h->KU, nS = (size_t)h->n_dev * h->KS;
   SG_CUDA_H(h->u.alloc(nU));
@@ -456,6 +510,10 @@ void sg_destroy(sg_solver* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->comm) cudaStreamDestroy(h->comm);
   delete h;
@@ -468,10 +526,15 @@ int sg_set_material(sg_solver* h, double density, double lam, double mu, const d
     return fail(SG_EINVAL, "sg_set_material: give both per-cell arrays or neither");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->stream));
+  const bool per_cell = lam_cell != nullptr;
+  const double* old_lam = h->lam.p;
+  const double* old_mu = h->mu.p;
+  bool changed = !h->have_material || per_cell != h->per_cell || density != h->density ||
+                 (!per_cell && (lam != h->lam_c || mu != h->mu_c));
   h->density = density;
   h->lam_c = lam;
   h->mu_c = mu;
-  h->per_cell = lam_cell != nullptr;
+  h->per_cell = per_cell;
   if (h->per_cell) {
     std::vector<double> l((size_t)h->n_owned_pad, 0.0), m((size_t)h->n_owned_pad, 0.0);
     std::memcpy(l.data(), lam_cell, (size_t)h->n_owned * 8);
@@ -480,9 +543,10 @@ int sg_set_material(sg_solver* h, double density, double lam, double mu, const d
     SG_CUDA(h->mu.alloc(m.size()));
     SG_CUDA(cudaMemcpy(h->lam.p, l.data(), l.size() * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(h->mu.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
+    changed = changed || h->lam.p != old_lam || h->mu.p != old_mu;
   }
   h->have_material = true;
-  h->config_version++;
+  if (changed) h->config_version++;   // kernel arguments are baked into the step graph
   return SG_OK;
 }
 
@@ -491,6 +555,7 @@ int sg_set_absorption(sg_solver* h, int64_t n, const int64_t* cell, const double
   if (n < 0 || (n > 0 && (!cell || !mats))) return fail(SG_EINVAL, "sg_set_absorption: bad arguments");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->stream));
+  if (n == 0 && h->nabs_pad == 0) return SG_OK;
   h->config_version++;
   if (n == 0) {
     h->nabs_pad = 0;
@@ -521,6 +586,7 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
     return fail(SG_EINVAL, "sg_set_source: bad arguments");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->stream));
+  if ((nsrc == 0 || nsteps == 0) && h->nsrc == 0) return SG_OK;
   h->config_version++;
   h->nsrc = 0;
   h->src_steps = 0;
@@ -549,13 +615,13 @@ int sg_set_state(sg_solver* h, const double* u, const double* s) {
   SG_CUDA(cudaSetDevice(h->device));
   // the scratch fields double as staging buffers: they are dead between time steps
   if (u) {
-    SG_CUDA(cudaMemcpyAsync(h->uh.p, u, (size_t)h->n_total * h->KU * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = relayout(h, h->u.p, h->uh.p, h->dim, true, h->stream);
+    SG_CUDA(cudaMemcpyAsync(h->uh.p, u, (size_t)h->n_owned * h->KU * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = relayout(h, h->u.p, h->uh.p, h->dim, true, h->stream, h->n_owned);
     if (rc) return rc;
   }
   if (s) {
-    SG_CUDA(cudaMemcpyAsync(h->sh.p, s, (size_t)h->n_total * h->KS * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, true, h->stream);
+    SG_CUDA(cudaMemcpyAsync(h->sh.p, s, (size_t)h->n_owned * h->KS * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, true, h->stream, h->n_owned);
     if (rc) return rc;
   }
   SG_CUDA(cudaStreamSynchronize(h->stream));
@@ -566,15 +632,16 @@ int sg_get_state(sg_solver* h, double* u, double* s) {
   if (!h) return fail(SG_EINVAL, "null solver");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->comm));
+  // owned cells only; the scratch fields double as staging buffers (dead between time steps)
   if (u) {
-    int rc = relayout(h, h->u.p, h->uh.p, h->dim, false, h->stream);
+    int rc = relayout(h, h->u.p, h->uh.p, h->dim, false, h->stream, h->n_owned);
     if (rc) return rc;
-    SG_CUDA(cudaMemcpyAsync(u, h->uh.p, (size_t)h->n_total * h->KU * 8, cudaMemcpyDeviceToHost, h->stream));
+    SG_CUDA(cudaMemcpyAsync(u, h->uh.p, (size_t)h->n_owned * h->KU * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   if (s) {
-    int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, false, h->stream);
+    int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, false, h->stream, h->n_owned);
     if (rc) return rc;
-    SG_CUDA(cudaMemcpyAsync(s, h->sh.p, (size_t)h->n_total * h->KS * 8, cudaMemcpyDeviceToHost, h->stream));
+    SG_CUDA(cudaMemcpyAsync(s, h->sh.p, (size_t)h->n_owned * h->KS * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   SG_CUDA(cudaStreamSynchronize(h->stream));
   return SG_OK;
@@ -589,7 +656,7 @@ int sg_get_field(sg_solver* h, int which, double* out) {
   const int nc = field_ncomp(h, which);
   DevBuf<double> tmp;   // test/diagnostic path: a private staging buffer keeps all four fields intact
   SG_CUDA(tmp.alloc((size_t)h->n_total * h->nd * nc));
-  int rc = relayout(h, f->p, tmp.p, nc, false, h->stream);
+  int rc = relayout(h, f->p, tmp.p, nc, false, h->stream, h->n_total);
   if (rc == SG_OK) {
     cudaError_t e = cudaMemcpyAsync(out, tmp.p, tmp.n * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -621,7 +688,10 @@ int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
     cudaGraph_t g = nullptr;
     SG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = SG_OK;
-    for (int k = 1; k <= 6 && rc == SG_OK; ++k) rc = launch_stage(h, k, SG_PART_ALL, dt, st);
+    if (h->npeers > 0)
+      rc = enqueue_step_peers(h, dt);
+    else
+      for (int k = 1; k <= 6 && rc == SG_OK; ++k) rc = launch_stage(h, k, SG_PART_ALL, dt, st);
     if (rc == SG_OK && h->nsrc > 0) sg::bump_step_kernel<<<1, 1, 0, st>>>(h->step_dev.p);
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc != SG_OK) {
@@ -749,6 +819,84 @@ void* sg_field_ptr(sg_solver* h, int which) {
   if (!h) return nullptr;
   DevBuf<double>* f = field_buf(h, which);
   return f ? (void*)f->p : nullptr;
+}
+
+int sg_ipc_export(sg_solver* h, unsigned char* out) {
+  if (!h || !out) return fail(SG_EINVAL, "sg_ipc_export: null argument");
+  SG_CUDA(cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == SG_IPC_HANDLE_BYTES, "handle size");
+  void* bufs[5] = {h->u.p, h->s.p, h->uh.p, h->sh.p, h->ctl.p};
+  for (int i = 0; i < 5; ++i) {
+    cudaIpcMemHandle_t mh;
+    SG_CUDA(cudaIpcGetMemHandle(&mh, bufs[i]));
+    std::memcpy(out + (size_t)i * SG_IPC_HANDLE_BYTES, &mh, SG_IPC_HANDLE_BYTES);
+  }
+  return SG_OK;
+}
+
+int sg_peer_connect(sg_solver* h, int32_t npeers, const sg_peer_desc* peers) {
+  if (!h || npeers < 0 || npeers > 16 || (npeers > 0 && !peers)) return fail(SG_EINVAL, "sg_peer_connect: bad arguments");
+  SG_CUDA(cudaSetDevice(h->device));
+  SG_CUDA(cudaStreamSynchronize(h->stream));
+  SG_CUDA(cudaStreamSynchronize(h->comm));
+  h->config_version++;
+  h->npeers = 0;
+  if (npeers == 0) return SG_OK;
+  std::vector<double*> rf((size_t)4 * npeers);
+  std::vector<unsigned long long*> fl((size_t)npeers);
+  std::vector<int64_t> dst((size_t)h->nsend, -1);
+  std::vector<int32_t> who((size_t)h->nsend, -1);
+  for (int i = 0; i < npeers; ++i) {
+    const sg_peer_desc& d = peers[i];
+    if (d.send_offset < 0 || d.send_count < 0 || d.send_offset + d.send_count > h->nsend || d.flag_slot < 0 ||
+        d.flag_slot >= 16 || d.remote_first_cell < 0)
+      return fail(SG_EINVAL, "sg_peer_connect: bad peer descriptor");
+    void* ptrs[5];
+    for (int b = 0; b < 5; ++b) {
+      cudaIpcMemHandle_t mh;
+      std::memcpy(&mh, d.handles[b], SG_IPC_HANDLE_BYTES);
+      cudaError_t e = cudaIpcOpenMemHandle(&ptrs[b], mh, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(SG_ECUDA, std::string("cudaIpcOpenMemHandle (peer rank ") + std::to_string(d.rank) + "): " +
+                                  cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptrs[b]);
+    }
+    for (int b = 0; b < 4; ++b) rf[(size_t)b * npeers + i] = (double*)ptrs[b];
+    fl[(size_t)i] = (unsigned long long*)ptrs[4] + d.flag_slot;
+    for (int64_t k = 0; k < d.send_count; ++k) {
+      dst[(size_t)(d.send_offset + k)] = d.remote_first_cell + k;
+      who[(size_t)(d.send_offset + k)] = i;
+    }
+  }
+  for (int64_t k = 0; k < h->nsend; ++k)
+    if (who[(size_t)k] < 0) return fail(SG_EINVAL, "sg_peer_connect: a send cell has no destination");
+  SG_CUDA(h->rfield.alloc(rf.size()));
+  SG_CUDA(h->rflag.alloc(fl.size()));
+  SG_CUDA(h->send_dst.alloc(dst.size()));
+  SG_CUDA(h->send_peer.alloc(who.size()));
+  SG_CUDA(cudaMemcpy(h->rfield.p, rf.data(), rf.size() * sizeof(double*), cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemcpy(h->rflag.p, fl.data(), fl.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemcpy(h->send_dst.p, dst.data(), dst.size() * 8, cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemcpy(h->send_peer.p, who.data(), who.size() * 4, cudaMemcpyHostToDevice));
+  h->npeers = npeers;
+  return SG_OK;
+}
+
+int sg_exchange(sg_solver* h, int which) {
+  if (!h || !field_buf(h, which)) return fail(SG_EINVAL, "sg_exchange: bad arguments");
+  SG_CUDA(cudaSetDevice(h->device));
+  return enqueue_exchange(h, which, h->stream);
+}
+
+int sg_peer_error(sg_solver* h, int64_t* err) {
+  if (!h || !err) return fail(SG_EINVAL, "sg_peer_error: null argument");
+  SG_CUDA(cudaSetDevice(h->device));
+  SG_CUDA(cudaStreamSynchronize(h->stream));
+  SG_CUDA(cudaStreamSynchronize(h->comm));
+  unsigned long long v = 0;
+  SG_CUDA(cudaMemcpy(&v, h->ctl.p + sg::SG_CTL_ERROR, 8, cudaMemcpyDeviceToHost));
+  *err = (int64_t)v;
+  return SG_OK;
 }
 
 void* sg_host_alloc(int64_t bytes) {

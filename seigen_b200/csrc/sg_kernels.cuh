@@ -433,4 +433,69 @@ __global__ void unpack_kernel(double* __restrict__ field, int64_t e0, int64_t n,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// peer-memory halo exchange (one process per GPU, buffers mapped through CUDA IPC over NVLink)
+// ---------------------------------------------------------------------------------------------
+// Writes field rows of my cut-adjacent cells straight into the halo tiles of the owning peers' copy of the same
+// field.  idx = k * n + c: consecutive threads write consecutive halo cells of one row (coalesced NVLink stores).
+__global__ void push_kernel(const double* __restrict__ field, const int64_t* __restrict__ cells,
+                            const int64_t* __restrict__ dst_cell, const int32_t* __restrict__ peer_of,
+                            double* const* __restrict__ rfield, int64_t n, int K, int tile) {
+  const int64_t total = n * K;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = idx % n;
+    const int k = (int)(idx / n);
+    const int64_t e = cells[c], r = dst_cell[c];
+    double* dst = rfield[peer_of[c]];
+    dst[((r / tile) * K + k) * tile + r % tile] = field[((e / tile) * K + k) * tile + e % tile];
+  }
+}
+
+// ctl layout (uint64): [0, 16) flags written by my peers, [16] exchanges I have signalled, [17] exchanges I have
+// waited for, [18] error word (1 = a wait timed out)
+constexpr int SG_CTL_SENT = 16, SG_CTL_WAITED = 17, SG_CTL_ERROR = 18, SG_CTL_WORDS = 32;
+
+// After push_kernel (stream order): make the pushed rows visible system-wide, then publish the new epoch in every
+// peer's flag slot for me.
+__global__ void signal_kernel(unsigned long long* ctl, unsigned long long* const* __restrict__ rflag, int npeers) {
+  __shared__ unsigned long long epoch;
+  if (threadIdx.x == 0) {
+    epoch = ctl[SG_CTL_SENT] + 1;
+    ctl[SG_CTL_SENT] = epoch;
+  }
+  __syncthreads();
+  __threadfence_system();
+  if ((int)threadIdx.x < npeers) {
+    unsigned long long* f = rflag[threadIdx.x];
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+  }
+}
+
+// Spins until every peer has published the epoch this rank is about to consume (bounded: sets the error word
+// instead of hanging if a peer never arrives).
+__global__ void wait_kernel(unsigned long long* ctl, int npeers, long long timeout_cycles) {
+  __shared__ unsigned long long epoch;
+  if (threadIdx.x == 0) {
+    epoch = ctl[SG_CTL_WAITED] + 1;
+    ctl[SG_CTL_WAITED] = epoch;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < npeers) {
+    const unsigned long long* f = ctl + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > timeout_cycles) {
+        ctl[SG_CTL_ERROR] = 1;
+        break;
+      }
+      __nanosleep(200);
+    } while (true);
+  }
+  __threadfence_system();
+}
+
 }  // namespace sg

@@ -133,6 +133,7 @@ class ExplicitElasticLF4(ElasticLF4):
         super(ExplicitElasticLF4, self).__init__(*args, **kwargs)
         self._dev = None
         self._halo = None
+        self.halo_mode = None
         self.steps_done = 0
         self.last_run_ms = None
 
@@ -146,10 +147,21 @@ class ExplicitElasticLF4(ElasticLF4):
             device = torch.cuda.current_device()
             self._dev = DeviceSolver(self.mesh, self.S.degree, device=device, plan=plan)
             if plan.nranks > 1:
-                from .halo import HaloExchanger
-                nd, d = self.S.elem.nd, self.dimension
-                self._halo = HaloExchanger(plan, nd * d * d, torch.device("cuda", device))
-                self._comm_stream = torch.cuda.ExternalStream(lib.sg_stream(self._dev.handle, 1), device=device)
+                import os
+                self.halo_mode = os.environ.get("SG_HALO", "peer")
+                if self.halo_mode == "peer":
+                    # rows go straight into the neighbours' halo tiles over NVLink (CUDA IPC); the whole step,
+                    # exchanges included, is one CUDA graph
+                    from .halo import connect_peers
+                    connect_peers(self._dev, plan)
+                elif self.halo_mode == "nccl":
+                    # library transport: pack -> NCCL send/recv -> unpack, driven pass by pass from the host
+                    from .halo import HaloExchanger
+                    nd, d = self.S.elem.nd, self.dimension
+                    self._halo = HaloExchanger(plan, nd * d * d, torch.device("cuda", device))
+                    self._comm_stream = torch.cuda.ExternalStream(lib.sg_stream(self._dev.handle, 1), device=device)
+                else:
+                    raise ValueError("SG_HALO must be 'peer' or 'nccl'")
         return self._dev
 
     def setup(self, times=None):
@@ -238,37 +250,23 @@ class ExplicitElasticLF4(ElasticLF4):
             self._source_key = key
 
     # -- state transfer ------------------------------------------------------------------------------------------
-    def _padded(self, f, shape):
-        dev = self._dev
-        nd = self.S.elem.nd
-        if dev.n_total == dev.n_owned:
-            return np.ascontiguousarray(f.dat.data)
-        out = np.zeros((dev.n_total * nd,) + shape)
-        out[:dev.n_owned * nd] = f.dat.data
-        return out
-
     def _upload_state(self):
-        d = self.dimension
-        u = self._padded(self.u0, (d,))
-        s = self._padded(self.s0, (d, d))
+        # u0 / s0 may be pending copies of u1 / s1 from the previous run(): upload from where the bytes are
+        u = self.u0.dat.current_source().data
+        s = self.s0.dat.current_source().data
         check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+        if self._dev.plan.nranks > 1 and self._halo is None:
+            check(lib.sg_exchange(self._dev.handle, capi.FIELD_U))
+            check(lib.sg_exchange(self._dev.handle, capi.FIELD_S))
         if self._halo is not None:
             self._exchange(capi.FIELD_U)
             self._exchange(capi.FIELD_S)
             check(lib.sg_compute_wait_comm(self._dev.handle))
 
     def _download_state(self):
-        dev, d, nd = self._dev, self.dimension, self.S.elem.nd
-        if dev.n_total == dev.n_owned:
-            check(lib.sg_get_state(dev.handle, ptr(self.u1.dat.data), ptr(self.s1.dat.data)))
-        else:
-            u = np.empty((dev.n_total * nd, d))
-            s = np.empty((dev.n_total * nd, d, d))
-            check(lib.sg_get_state(dev.handle, ptr(u), ptr(s)))
-            self.u1.dat.data[...] = u[:dev.n_owned * nd]
-            self.s1.dat.data[...] = s[:dev.n_owned * nd]
-        np.copyto(self.u0.dat.data, self.u1.dat.data)      # elastic.py:296
-        np.copyto(self.s0.dat.data, self.s1.dat.data)      # elastic.py:304
+        check(lib.sg_get_state(self._dev.handle, ptr(self.u1.dat.data), ptr(self.s1.dat.data)))
+        self.u0.dat.defer_copy_from(self.u1.dat)           # u0.assign(u1), elastic.py:296 (copied on first access)
+        self.s0.dat.defer_copy_from(self.s1.dat)           # s0.assign(s1), elastic.py:304
 
     # -- multi-GPU stage loop ------------------------------------------------------------------------------------
     def _exchange(self, which):
@@ -312,7 +310,8 @@ class ExplicitElasticLF4(ElasticLF4):
         self.setup(times)
         dev = self._dev
         with timed_region('timestepping'):
-            self._upload_state()
+            with timed_region('state upload'):
+                self._upload_state()
             if self.output:
                 for n in range(len(times)):
                     self._advance(1, n)

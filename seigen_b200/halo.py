@@ -14,7 +14,41 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["HaloExchanger"]
+__all__ = ["HaloExchanger", "connect_peers"]
+
+
+def connect_peers(dev, plan, group=None):
+    """Wire the peer-memory exchange of ``include/seigen_b200.h`` (sg_ipc_export / sg_peer_connect): every rank
+    publishes the CUDA-IPC handles of its four fields and its control words together with where each neighbour's
+    cells land in its halo; torch.distributed is only the bootstrap channel (any backend)."""
+    import ctypes as C
+
+    from . import capi
+    from .capi import check, lib
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    raw = (C.c_ubyte * (5 * 64))()
+    check(lib.sg_ipc_export(dev.handle, raw))
+    mine = {"handles": bytes(raw), "n_owned": int(plan.n_owned), "recv": {int(q): tuple(v) for q, v in plan.recv.items()},
+            "peers": sorted(int(q) for q in plan.recv)}
+    infos = [None] * world
+    dist.all_gather_object(infos, mine, group=group)
+    tile = lib.sg_tile_cells(dev.dim, dev.degree)
+    peers = mine["peers"]
+    descs = (capi.PeerDesc * max(len(peers), 1))()
+    for i, q in enumerate(peers):
+        qi = infos[q]
+        first, count = qi["recv"][rank]
+        so, sn = plan.send_offsets[q]
+        if sn != count:
+            raise capi.SgError(f"halo plan mismatch between ranks {rank} and {q}: send {sn} cells, peer expects {count}")
+        d = descs[i]
+        d.rank, d.flag_slot = q, qi["peers"].index(rank)
+        d.send_offset, d.send_count = so, sn
+        d.remote_first_cell = -(-qi["n_owned"] // tile) * tile + first
+        C.memmove(d.handles, qi["handles"], 5 * 64)
+    check(lib.sg_peer_connect(dev.handle, len(peers), descs))
+    dist.barrier(group=group)
 
 
 class HaloExchanger:
