@@ -2,6 +2,7 @@
 #include "../../include/seigen_b200.h"
 #include "sg_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -29,17 +30,23 @@ int fail(int code, const std::string& msg) {
 
 // ---- per-element kernel configuration ------------------------------------------------------
 struct Variant {
-  int dim, degree, nd, nfp, tile, split, minb;
-  size_t smem_f, smem_g;
+  int dim, degree, nd, nfp, tile, split, minb, ns_plain, ns_axpy, axs;
+  sg::StagePlan (*plan_f)(bool classes, bool mat, bool sponge);
+  sg::StagePlan (*plan_f_axpy)(bool classes, bool mat, bool sponge);
+  sg::StagePlan (*plan_g)(bool classes, bool mat, bool sponge);
+  sg::StagePlan (*plan_g_axpy)(bool classes, bool mat, bool sponge);
   const void* f_plain;
   const void* f_axpy;
   const void* g_plain;
   const void* g_axpy;
 };
 
-template <int D, int P, int TILE, int SPLIT, int MINB> Variant make_variant() {
+// TILE cells per tile, SPLIT threads per cell, MINB / MINBA CTAs per SM the compiler must allow for the plain / AXPY
+// kernels (register cap), NSP / NSA pipeline depth of the plain / AXPY kernels, AXS: stage the AXPY operands through
+// shared memory (bulk copies) instead of reading them from L2, XREG: G-type gradients in registers (SPLIT == 1)
+template <int D, int P, int TILE, int SPLIT, int MINB, int MINBA, int NSP, int NSA, bool AXS, bool XREG>
+Variant make_variant() {
   using E = ElemOps<D, P>;
-  using L = sg::SmemLayout<D, P, TILE>;
   Variant v;
   v.dim = D;
   v.degree = P;
@@ -48,28 +55,42 @@ template <int D, int P, int TILE, int SPLIT, int MINB> Variant make_variant() {
   v.tile = TILE;
   v.split = SPLIT;
   v.minb = MINB;
-  v.smem_f = L::f_bytes;
-  v.smem_g = L::g_bytes;
-  v.f_plain = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, false>;
-  v.f_axpy = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, true>;
-  v.g_plain = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, false>;
-  v.g_axpy = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, true>;
+  v.ns_plain = NSP;
+  v.ns_axpy = NSA;
+  v.axs = AXS;
+  v.plan_f = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, false, false>(c, m, sp, E::FTAB_SIZE); };
+  v.plan_f_axpy = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, false, AXS>(c, m, sp, E::FTAB_SIZE); };
+  v.plan_g = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, true, false, !XREG>(c, m, sp, E::FTAB_SIZE); };
+  v.plan_g_axpy = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, true, AXS, !XREG>(c, m, sp, E::FTAB_SIZE); };
+  v.f_plain = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false>;
+  v.f_axpy = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS>;
+  v.g_plain = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false, XREG>;
+  v.g_axpy = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS, XREG>;
   return v;
 }
 
 const std::vector<Variant>& variants() {
   static const std::vector<Variant> v = {
       // first entry of each (dim, degree) is the default; the others are tuning candidates selectable with
-      // SG_TILE / SG_SPLIT / SG_MINB (scripts/perf_probe.py)
-      make_variant<2, 1, 64, 1, 12>(), make_variant<2, 1, 64, 1, 16>(), make_variant<2, 1, 128, 1, 6>(),
-      make_variant<2, 1, 128, 1, 8>(),
-      make_variant<2, 2, 64, 1, 10>(), make_variant<2, 2, 64, 1, 12>(), make_variant<2, 2, 64, 1, 16>(),
-      make_variant<2, 2, 128, 1, 5>(), make_variant<2, 2, 128, 1, 6>(), make_variant<2, 2, 32, 1, 20>(),
-      make_variant<2, 3, 64, 1, 8>(),
-      make_variant<2, 4, 32, 1, 6>(),
-      make_variant<3, 1, 64, 1, 8>(), make_variant<3, 1, 64, 1, 12>(), make_variant<3, 1, 32, 1, 16>(),
-      make_variant<3, 2, 32, 3, 4>(),
-      make_variant<3, 3, 32, 3, 2>(),
+      // SG_TILE / SG_SPLIT / SG_MINB / SG_NS (scripts/perf_probe.py)
+      //            D  P  TILE SPLIT MINB MINBA NSP NSA AXS   XREG
+      make_variant<2, 1, 64, 1, 8, 4, 2, 2, true, true>(),
+      make_variant<2, 1, 64, 1, 10, 4, 2, 2, true, true>(),
+      make_variant<2, 1, 128, 1, 4, 2, 2, 2, true, true>(),
+      make_variant<2, 2, 64, 1, 8, 3, 2, 2, true, true>(),
+      make_variant<2, 2, 64, 1, 10, 3, 2, 2, true, true>(),
+      make_variant<2, 2, 64, 1, 8, 3, 3, 2, true, true>(),
+      make_variant<2, 2, 64, 1, 6, 3, 3, 2, true, false>(),
+      make_variant<2, 2, 128, 1, 4, 2, 2, 2, true, true>(),
+      make_variant<2, 2, 64, 2, 4, 3, 2, 2, true, false>(),
+      make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>(),
+      make_variant<2, 3, 32, 1, 8, 4, 2, 2, true, true>(),
+      make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>(),
+      make_variant<3, 1, 64, 1, 4, 3, 2, 2, true, false>(),
+      make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>(),
+      make_variant<3, 1, 32, 3, 4, 4, 3, 2, true, false>(),
+      make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>(),
+      make_variant<3, 3, 32, 3, 2, 2, 2, 1, false, false>(),
   };
   return v;
 }
@@ -80,12 +101,13 @@ int env_int(const char* name) {
 }
 
 const Variant* find_variant(int dim, int degree) {
-  const int tile = env_int("SG_TILE"), split = env_int("SG_SPLIT"), minb = env_int("SG_MINB");
+  const int tile = env_int("SG_TILE"), split = env_int("SG_SPLIT"), minb = env_int("SG_MINB"), ns = env_int("SG_NS");
   const Variant* first = nullptr;
   for (const Variant& v : variants()) {
     if (v.dim != dim || v.degree != degree) continue;
     if (!first) first = &v;
-    if ((tile == 0 || v.tile == tile) && (split == 0 || v.split == split) && (minb == 0 || v.minb == minb))
+    if ((tile == 0 || v.tile == tile) && (split == 0 || v.split == split) && (minb == 0 || v.minb == minb) &&
+        (ns == 0 || v.ns_plain * 10 + v.ns_axpy == ns))
       return &v;
   }
   return first;
@@ -117,12 +139,17 @@ struct sg_solver {
   int64_t n_owned = 0, n_total = 0, n_owned_pad = 0, n_halo = 0, n_dev = 0, n_boundary = 0;
   int tiles_owned = 0, tiles_total = 0, tiles_boundary = 0;
   DevBuf<double> u, s, uh, sh;          // state + scratch, tile-blocked
-  DevBuf<double> geo, geotab, lam, mu, absmat, amp;
+  DevBuf<double> geo, geotab, mat, absmat, amp;
   DevBuf<uint16_t> geoidx;
   int64_t n_geo_classes = 0;
   DevBuf<int32_t> nbr, absidx;
   DevBuf<uint8_t> code;
-  DevBuf<int64_t> src_addr, step_dev, send_cells;
+  DevBuf<int64_t> step_dev, send_cells;
+  DevBuf<int32_t> src_start, src_off;
+  DevBuf<unsigned int> sched;             // [3 parts][2] dynamic tile scheduler words (sg::sched_next)
+  int nsm = 148;
+  int occ[4] = {0, 0, 0, 0};            // resident CTAs per SM of f_plain, f_axpy, g_plain, g_axpy
+  uint32_t occ_smem[4] = {0, 0, 0, 0};  // the shared-memory size those were computed for
   int64_t nabs_pad = 0, nsrc = 0, src_steps = 0, nsend = 0;
   bool have_material = false, per_cell = false;
   double density = 1.0, lam_c = 0.0, mu_c = 0.0;
@@ -165,13 +192,13 @@ sg::StageParams base_params(sg_solver* h) {
   p.geo = h->geo.p;
   p.geoidx = h->geoidx.p;
   p.geotab = h->geotab.p;
+  p.nclass = (int32_t)h->n_geo_classes;
   p.nbr = h->nbr.p;
   p.code = h->code.p;
   p.absidx = h->nabs_pad > 0 ? h->absidx.p : nullptr;
   p.absmat = h->absmat.p;
   p.nabs_pad = h->nabs_pad;
-  p.lam = h->per_cell ? h->lam.p : nullptr;
-  p.mu = h->per_cell ? h->mu.p : nullptr;
+  p.mat = h->per_cell ? h->mat.p : nullptr;
   p.lam_c = h->lam_c;
   p.mu_c = h->mu_c;
   return p;
@@ -190,53 +217,70 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
   const Variant* v = h->var;
   sg::StageParams p = base_params(h);
   p.tile0 = t0;
+  p.ntiles = nt;
+  p.sched = h->sched.p + 2 * part;
   const double c3 = dt * dt * dt / 24.0;
+  const bool classes = h->geoidx.p != nullptr, sponge = p.absidx != nullptr, mat = p.mat != nullptr;
   const void* fn = nullptr;
-  size_t smem = 0;
+  sg::StagePlan pl{};
+  int* occ = nullptr;
+  bool gtype = false;
   switch (stage) {
     case 1:  // uh1 = Dv(s0) - P(sigma, u0)                         elastic.py:157-161, 292
       p.in = h->s.p; p.out = h->uh.p; p.absu = h->u.p;
-      fn = v->f_plain; smem = v->smem_f;
+      fn = v->f_plain; pl = v->plan_f(classes, mat, sponge); occ = &h->occ[0];
       break;
     case 2:  // stemp = Ds(uh1) + src                               elastic.py:163-167, 293
-      p.in = h->uh.p; p.out = h->sh.p;
-      fn = v->g_plain; smem = v->smem_g;
+      p.in = h->uh.p; p.out = h->sh.p; p.src_scale = 1.0; gtype = true;
+      fn = v->g_plain; pl = v->plan_g(classes, mat, sponge); occ = &h->occ[2];
       break;
     case 3:  // u1 = rho*u0 + dt*uh1 + dt^3/24*(Dv(stemp) - P(sigma, u0))   elastic.py:169-173, 341-345, 294-296
       p.in = h->sh.p; p.out = h->u.p; p.ax0 = h->u.p; p.ax1 = h->uh.p; p.absu = h->u.p;
       p.c0 = h->density; p.c1 = dt; p.c2 = c3;
-      fn = v->f_axpy; smem = v->smem_f;
+      fn = v->f_axpy; pl = v->plan_f_axpy(classes, mat, sponge); occ = &h->occ[1];
       break;
     case 4:  // sh1 = Ds(u1) + src                                  elastic.py:181-185, 300
-      p.in = h->u.p; p.out = h->sh.p;
-      fn = v->g_plain; smem = v->smem_g;
+      p.in = h->u.p; p.out = h->sh.p; p.src_scale = 1.0; gtype = true;
+      fn = v->g_plain; pl = v->plan_g(classes, mat, sponge); occ = &h->occ[2];
       break;
     case 5:  // utemp = Dv(sh1) - P(sigma, u1)                      elastic.py:187-191, 301
       p.in = h->sh.p; p.out = h->uh.p; p.absu = h->u.p;
-      fn = v->f_plain; smem = v->smem_f;
+      fn = v->f_plain; pl = v->plan_f(classes, mat, sponge); occ = &h->occ[0];
       break;
     case 6:  // s1 = s0 + dt*sh1 + dt^3/24*(Ds(utemp) + src)        elastic.py:193-197, 348-352, 302-304
       p.in = h->uh.p; p.out = h->s.p; p.ax0 = h->s.p; p.ax1 = h->sh.p;
-      p.c0 = 1.0; p.c1 = dt; p.c2 = c3;
-      fn = v->g_axpy; smem = v->smem_g;
+      p.c0 = 1.0; p.c1 = dt; p.c2 = c3; p.src_scale = c3; gtype = true;
+      fn = v->g_axpy; pl = v->plan_g_axpy(classes, mat, sponge); occ = &h->occ[3];
       break;
     default:
       return fail(SG_EINVAL, "sg_stage: stage must be 1..6");
   }
-  if (nt > 0) {
-    void* args[] = {(void*)&p};
-    SG_CUDA(cudaLaunchKernel(fn, dim3(nt), dim3(v->tile * v->split), args, smem, st));
+  // source: added wherever g is evaluated (elastic.py:165, 183, 195), by the CTA that produced the tile
+  if (gtype && h->nsrc > 0) {
+    p.src_start = h->src_start.p;
+    p.src_off = h->src_off.p;
+    p.amp = h->amp.p;
+    p.step = h->step_dev.p;
+    p.nsteps = h->src_steps;
+    p.nsrc = h->nsrc;
   }
-  // source: added wherever g is evaluated (elastic.py:165, 183, 195), restricted to the tiles this launch covers
-  // so that boundary cells carry their source term before they are packed for the halo exchange.
-  if ((stage == 2 || stage == 4 || stage == 6) && h->nsrc > 0 && nt > 0) {
-    double* dst = stage == 6 ? h->s.p : h->sh.p;
-    const double scale = stage == 6 ? c3 : 1.0;
-    const int64_t tile_elems = (int64_t)h->KS * h->tile;
-    sg::add_source_kernel<<<grid_for(h->nsrc), 256, 0, st>>>(dst, h->src_addr.p, h->amp.p, h->step_dev.p,
-                                                             h->src_steps, h->nsrc, scale, t0 * tile_elems,
-                                                             (int64_t)(t0 + nt) * tile_elems);
-    SG_CUDA(cudaGetLastError());
+  if (nt > 0) {
+    const int nthreads = v->tile * v->split;
+    if (h->occ_smem[occ - h->occ] != pl.total) {   // (re)size the kernel's shared memory and its persistent grid
+      SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+      SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      int nb = 0;
+      SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, pl.total));
+      if (nb < 1) return fail(SG_ECUDA, "stage kernel does not fit on an SM (shared memory plan too large)");
+      *occ = nb;
+      h->occ_smem[occ - h->occ] = pl.total;
+    }
+    int grid = h->nsm * *occ;
+    const int cap = env_int("SG_GRID_PER_SM");
+    if (cap > 0) grid = h->nsm * cap;
+    if (grid > nt) grid = nt;
+    void* args[] = {(void*)&p};
+    SG_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(nthreads), args, pl.total, st));
   }
   return SG_OK;
 }
@@ -275,15 +319,16 @@ int enqueue_exchange(sg_solver* h, int which, cudaStream_t st) {
 
 const int STAGE_OUTPUT[7] = {-1, SG_FIELD_UH, SG_FIELD_SH, SG_FIELD_U, SG_FIELD_SH, SG_FIELD_UH, SG_FIELD_S};
 
-// One time step on a rank with peers: per pass, cut-adjacent tiles first, then their rows travel on the comm
-// stream (push -> signal -> wait) while the interior tiles are computed on the compute stream.
+// One time step on a rank with peers.  Per pass the (few) cut-adjacent tiles run on the comm stream, followed by
+// push -> signal -> wait, while the interior tiles run concurrently on the compute stream; the two branches join
+// before the next pass.  Both branches read the previous pass's output and write disjoint cells.
 int enqueue_step_peers(sg_solver* h, double dt) {
   cudaStream_t st = h->stream, cm = h->comm;
   for (int k = 1; k <= 6; ++k) {
-    int rc = launch_stage(h, k, SG_PART_BOUNDARY, dt, st);
-    if (rc) return rc;
     SG_CUDA(cudaEventRecord(h->ev_fork, st));
     SG_CUDA(cudaStreamWaitEvent(cm, h->ev_fork, 0));
+    int rc = launch_stage(h, k, SG_PART_BOUNDARY, dt, cm);
+    if (rc) return rc;
     rc = enqueue_exchange(h, STAGE_OUTPUT[k], cm);
     if (rc) return rc;
     rc = launch_stage(h, k, SG_PART_INTERIOR, dt, st);
@@ -381,6 +426,8 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  SG_CUDA_H(h->sched.alloc(8));
+  SG_CUDA_H(cudaMemsetAsync(h->sched.p, 0, 8 * sizeof(unsigned int), h->stream));
   SG_CUDA_H(h->ctl.alloc(sg::SG_CTL_WORDS));
   SG_CUDA_H(cudaMemsetAsync(h->ctl.p, 0, sg::SG_CTL_WORDS * 8, h->stream));
 
@@ -483,13 +530,10 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
     SG_CUDA_H(cudaMemcpy(h->geo.p, geo.data(), geo.size() * 8, cudaMemcpyHostToDevice));
   }
 
-  for (const void* fn : {v->f_plain, v->f_axpy}) {
-    SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem_f));
-    SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
-  for (const void* fn : {v->g_plain, v->g_axpy}) {
-    SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem_g));
-    SG_CUDA_H(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  {
+    cudaDeviceProp prop;
+    SG_CUDA_H(cudaGetDeviceProperties(&prop, d->device));
+    h->nsm = prop.multiProcessorCount;
   }
   SG_CUDA_H(cudaStreamSynchronize(h->stream));
 #undef SG_CUDA_H
@@ -504,16 +548,16 @@ void sg_destroy(sg_solver* h) {
   if (h->comm) cudaStreamSynchronize(h->comm);
   drop_graph(h);
   h->u.release(); h->s.release(); h->uh.release(); h->sh.release();
-  h->geo.release(); h->geotab.release(); h->geoidx.release(); h->lam.release(); h->mu.release(); h->absmat.release(); h->amp.release();
+  h->geo.release(); h->geotab.release(); h->geoidx.release(); h->mat.release(); h->absmat.release(); h->amp.release();
   h->nbr.release(); h->absidx.release(); h->code.release();
-  h->src_addr.release(); h->step_dev.release(); h->send_cells.release();
+  h->src_start.release(); h->src_off.release(); h->step_dev.release(); h->send_cells.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_sync) cudaEventDestroy(h->ev_sync);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-  h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
+  h->sched.release(); h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->comm) cudaStreamDestroy(h->comm);
   delete h;
@@ -527,8 +571,7 @@ int sg_set_material(sg_solver* h, double density, double lam, double mu, const d
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->stream));
   const bool per_cell = lam_cell != nullptr;
-  const double* old_lam = h->lam.p;
-  const double* old_mu = h->mu.p;
+  const double* old_mat = h->mat.p;
   bool changed = !h->have_material || per_cell != h->per_cell || density != h->density ||
                  (!per_cell && (lam != h->lam_c || mu != h->mu_c));
   h->density = density;
@@ -536,14 +579,17 @@ int sg_set_material(sg_solver* h, double density, double lam, double mu, const d
   h->mu_c = mu;
   h->per_cell = per_cell;
   if (h->per_cell) {
-    std::vector<double> l((size_t)h->n_owned_pad, 0.0), m((size_t)h->n_owned_pad, 0.0);
-    std::memcpy(l.data(), lam_cell, (size_t)h->n_owned * 8);
-    std::memcpy(m.data(), mu_cell, (size_t)h->n_owned * 8);
-    SG_CUDA(h->lam.alloc(l.size()));
-    SG_CUDA(h->mu.alloc(m.size()));
-    SG_CUDA(cudaMemcpy(h->lam.p, l.data(), l.size() * 8, cudaMemcpyHostToDevice));
-    SG_CUDA(cudaMemcpy(h->mu.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
-    changed = changed || h->lam.p != old_lam || h->mu.p != old_mu;
+    // [tile][2][TILE]: lambda row then mu row of each tile, one bulk copy per tile
+    const int T = h->tile;
+    std::vector<double> m((size_t)h->n_owned_pad * 2, 0.0);
+    for (int64_t e = 0; e < h->n_owned; ++e) {
+      const size_t t = (size_t)e / T, l = (size_t)e % T;
+      m[(t * 2 + 0) * T + l] = lam_cell[e];
+      m[(t * 2 + 1) * T + l] = mu_cell[e];
+    }
+    SG_CUDA(h->mat.alloc(m.size()));
+    SG_CUDA(cudaMemcpy(h->mat.p, m.data(), m.size() * 8, cudaMemcpyHostToDevice));
+    changed = changed || h->mat.p != old_mat;
   }
   h->have_material = true;
   if (changed) h->config_version++;   // kernel arguments are baked into the step graph
@@ -592,19 +638,35 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
   h->src_steps = 0;
   if (nsrc == 0 || nsteps == 0) return SG_OK;
   const int dd = h->dim * h->dim;
-  std::vector<int64_t> addr((size_t)nsrc);
+  // entries sorted by tile: the G-type CTA that produces a tile adds that tile's source values (src_start/src_off)
+  std::vector<std::pair<int64_t, int64_t>> key((size_t)nsrc);   // (tile * tile_elems + offset, original column)
+  const int64_t tile_elems = (int64_t)h->KS * h->tile;
   for (int64_t k = 0; k < nsrc; ++k) {
     const int64_t dof = sdof[k];
     const int64_t cell = dof / ((int64_t)h->nd * dd);
     if (dof < 0 || cell >= h->n_owned) return fail(SG_EINVAL, "sg_set_source: dof outside owned cells");
     const int r = (int)(dof % ((int64_t)h->nd * dd));
     const int node = r / dd, comp = r % dd;
-    addr[(size_t)k] = ((cell / h->tile) * h->KS + comp * h->nd + node) * h->tile + cell % h->tile;
+    key[(size_t)k] = {(cell / h->tile) * tile_elems + (int64_t)(comp * h->nd + node) * h->tile + cell % h->tile, k};
   }
-  SG_CUDA(h->src_addr.alloc((size_t)nsrc));
-  SG_CUDA(h->amp.alloc((size_t)nsrc * nsteps));
-  SG_CUDA(cudaMemcpy(h->src_addr.p, addr.data(), (size_t)nsrc * 8, cudaMemcpyHostToDevice));
-  SG_CUDA(cudaMemcpy(h->amp.p, amp, (size_t)nsrc * nsteps * 8, cudaMemcpyHostToDevice));
+  std::sort(key.begin(), key.end());
+  for (int64_t k = 1; k < nsrc; ++k)
+    if (key[(size_t)k].first == key[(size_t)k - 1].first) return fail(SG_EINVAL, "sg_set_source: duplicate dof");
+  std::vector<int32_t> start((size_t)h->tiles_owned + 1, 0), off((size_t)nsrc);
+  std::vector<double> a((size_t)nsrc * nsteps);
+  for (int64_t k = 0; k < nsrc; ++k) {
+    const int64_t t = key[(size_t)k].first / tile_elems;
+    start[(size_t)t + 1]++;
+    off[(size_t)k] = (int32_t)(key[(size_t)k].first % tile_elems);
+    for (int64_t n = 0; n < nsteps; ++n) a[(size_t)(n * nsrc + k)] = amp[(size_t)(n * nsrc + key[(size_t)k].second)];
+  }
+  for (size_t t = 0; t < (size_t)h->tiles_owned; ++t) start[t + 1] += start[t];
+  SG_CUDA(h->src_start.alloc(start.size()));
+  SG_CUDA(h->src_off.alloc(off.size()));
+  SG_CUDA(h->amp.alloc(a.size()));
+  SG_CUDA(cudaMemcpy(h->src_start.p, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemcpy(h->src_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemcpy(h->amp.p, a.data(), a.size() * 8, cudaMemcpyHostToDevice));
   h->nsrc = nsrc;
   h->src_steps = nsteps;
   return SG_OK;

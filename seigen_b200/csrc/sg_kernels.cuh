@@ -36,16 +36,25 @@ struct StageParams {
   const double* geo;      // [tile][D*D][TILE]  Jinv per cell, or nullptr when geometry classes are used
   const uint16_t* geoidx; // [tile][TILE] class of each cell (affine-congruent cells share one Jinv)
   const double* geotab;   // [nclass][D*D]
+  int32_t nclass;
   const int32_t* nbr;     // [tile][NF][TILE]   neighbour cell (device index)
   const uint8_t* code;    // [tile][NF][TILE]
   const int32_t* absidx;  // [tile][TILE] row of absmat or -1; nullptr = no sponge anywhere
   const double* absmat;   // [ND*ND][nabs_pad]
   int64_t nabs_pad;
-  const double* lam;      // per cell [tile][TILE] or nullptr
-  const double* mu;
+  const double* mat;      // per cell [tile][2][TILE] (lambda, mu) or nullptr
   double lam_c, mu_c;
   double c0, c1, c2;      // AXPY: out = c0*ax0 + c1*ax1 + c2*rhs
+  // nodal source values added where g is evaluated (elastic.py:165, 183, 195, 285-288), G-type only
+  const int32_t* src_start;  // [tiles + 1] first source entry of each tile, or nullptr
+  const int32_t* src_off;    // [nsrc] offset inside the tile's K*TILE block
+  const double* amp;         // [nsteps][nsrc]
+  const int64_t* step;       // device-side step counter
+  int64_t nsteps, nsrc;
+  double src_scale;
   int32_t tile0;          // first tile of this launch
+  int32_t ntiles;         // tiles of this launch
+  unsigned int* sched;    // [2] dynamic tile scheduler of this launch: next ticket, CTAs finished (both 0 at launch)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -56,6 +65,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -66,9 +77,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -84,7 +92,54 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-template <int TILE> __device__ __forceinline__ int tile_of(int e) { return e / TILE; }
+// ---------------------------------------------------------------------------------------------
+// Shared-memory plan of one pipeline stage (= everything one tile needs, all of it brought in by bulk copies):
+//   input tile | [ax0 | ax1] | nbr | code | geometry (class ids or Jinv) | [lambda, mu] | [absidx]
+// and of the CTA-wide area behind the NS stages:  mbarriers + slot tile ids | facet node table | geometry class
+// table | [X].  The same function sizes the launch on the host and lays the buffers out on the device.
+// ---------------------------------------------------------------------------------------------
+constexpr int GEO_SMEM_CLASSES = 64;
+
+struct StagePlan {
+  uint32_t in, ax0, ax1, nbr, code, geo, mat, abs, stage_bytes;   // offsets inside a stage
+  uint32_t bars, ftab, gtab, x, total;                            // offsets from the start of shared memory
+  uint32_t in_b, ax_b, nbr_b, code_b, geo_b, mat_b, abs_b;        // copy sizes (0 = not copied)
+};
+
+__host__ __device__ constexpr uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
+__host__ __device__ constexpr uint32_t up128(uint32_t x) { return (x + 127u) & ~127u; }
+
+template <int D, int ND, int TILE, int NS, bool GTYPE, bool AXS, bool XS = GTYPE>
+__host__ __device__ inline StagePlan make_plan(bool classes, bool per_cell_mat, bool sponge, int ftab_size) {
+  constexpr uint32_t KS = D * D * ND, KU = D * ND, NF = D + 1;
+  constexpr uint32_t KIN = GTYPE ? KU : KS, KAX = GTYPE ? KS : KU;
+  StagePlan p{};
+  uint32_t o = 0;
+  p.in_b = KIN * TILE * 8;
+  p.in = o; o += p.in_b;
+  p.ax_b = AXS ? KAX * TILE * 8 : 0;
+  p.ax0 = o; o += p.ax_b;
+  p.ax1 = o; o += p.ax_b;
+  p.nbr_b = NF * TILE * 4;
+  p.nbr = o; o += p.nbr_b;
+  p.code_b = up16(NF * TILE);
+  p.code = o; o += p.code_b;
+  p.geo_b = classes ? up16(TILE * 2) : (uint32_t)(D * D * TILE * 8);
+  p.geo = o; o += p.geo_b;
+  p.mat_b = (GTYPE && per_cell_mat) ? 2 * TILE * 8 : 0;
+  p.mat = o; o += p.mat_b;
+  p.abs_b = (!GTYPE && sponge) ? up16(TILE * 4) : 0;
+  p.abs = o; o += p.abs_b;
+  p.stage_bytes = up128(o);
+  o = p.stage_bytes * NS;
+  p.bars = o; o += up16(8 * NS + 4 * NS);   // mbarriers, then the tile id of each slot
+  p.ftab = o; o += up16((uint32_t)ftab_size);
+  p.gtab = o; o += classes ? (uint32_t)(GEO_SMEM_CLASSES * D * D * 8) : 0;
+  o = up128(o);
+  p.x = o; o += (GTYPE && XS) ? KS * TILE * 8 : 0;
+  p.total = o;
+  return p;
+}
 
 // ---------------------------------------------------------------------------------------------
 // contexts handed to the generated contractions
@@ -185,190 +240,316 @@ template <int D, int ND, int NFP, int TILE> struct GCtx {
   }
 };
 
-template <int D, int P, int TILE> struct SmemLayout {
-  using E = ElemOps<D, P>;
-  static constexpr int KS = D * D * E::ND, KU = D * E::ND;
-  static constexpr size_t tail = 16 + ((E::FTAB_SIZE + 15) / 16) * 16;   // mbarrier + ftab
-  static constexpr size_t f_bytes = (size_t)KS * TILE * 8 + tail;
-  static constexpr size_t g_bytes = (size_t)(KU + KS) * TILE * 8 + tail;
-};
-
 // ---------------------------------------------------------------------------------------------
-// common prologue: start the bulk copy of the input tile, fetch per-cell geometry meanwhile
+// producer side: one thread starts every bulk copy of a tile; they all complete on the stage's mbarrier
 // ---------------------------------------------------------------------------------------------
-template <int D, int ND, int NFP, int TILE, int KIN, int KAX, int NTHREADS, int FTAB_SIZE>
-__device__ __forceinline__ void stage_prologue(const StageParams& p, int tile, int lane, double* sIn,
-                                               uint64_t* bar, unsigned char* sft, const unsigned char* ftab,
-                                               FaceGeom<D, ND, NFP, TILE>& g) {
-  constexpr int NF = D + 1;
-  const int tid = threadIdx.x;
-  if (tid == 0) mbar_init(bar, 1);
-  for (int i = tid; i < FTAB_SIZE; i += NTHREADS) sft[i] = ftab[i];
-  __syncthreads();
-  if (tid == 0) {
-    constexpr uint32_t BYTES = KIN * TILE * 8;
-    mbar_expect_tx(bar, BYTES);
-    bulk_g2s(sIn, p.in + (size_t)tile * (KIN * TILE), BYTES, bar);
-    if (KAX > 0) {   // LF4 combination operands: start their DRAM reads now, consume them from L2 in the epilogue
-      prefetch_l2(p.ax0 + (size_t)tile * (KAX * TILE), KAX * TILE * 8);
-      prefetch_l2(p.ax1 + (size_t)tile * (KAX * TILE), KAX * TILE * 8);
-    }
+template <int D, int ND, int TILE, bool GTYPE>
+__device__ __forceinline__ void issue_tile(const StageParams& p, const StagePlan& pl, unsigned char* stage,
+                                           uint64_t* bar, int tile) {
+  constexpr int KS = D * D * ND, KU = D * ND, NF = D + 1;
+  constexpr int KIN = GTYPE ? KU : KS, KAX = GTYPE ? KS : KU;
+  const uint32_t total = pl.in_b + 2 * pl.ax_b + pl.nbr_b + pl.code_b + pl.geo_b + pl.mat_b + pl.abs_b;
+  mbar_expect_tx(bar, total);
+  bulk_g2s(stage + pl.in, p.in + (size_t)tile * (KIN * TILE), pl.in_b, bar);
+  if (pl.ax_b) {
+    bulk_g2s(stage + pl.ax0, p.ax0 + (size_t)tile * (KAX * TILE), pl.ax_b, bar);
+    bulk_g2s(stage + pl.ax1, p.ax1 + (size_t)tile * (KAX * TILE), pl.ax_b, bar);
   }
+  bulk_g2s(stage + pl.nbr, p.nbr + (size_t)tile * (NF * TILE), pl.nbr_b, bar);
+  bulk_g2s(stage + pl.code, p.code + (size_t)tile * pl.code_b, pl.code_b, bar);
+  if (p.geoidx != nullptr)
+    bulk_g2s(stage + pl.geo, p.geoidx + (size_t)tile * (pl.geo_b / 2), pl.geo_b, bar);
+  else
+    bulk_g2s(stage + pl.geo, p.geo + (size_t)tile * (D * D * TILE), pl.geo_b, bar);
+  if (pl.mat_b) bulk_g2s(stage + pl.mat, p.mat + (size_t)tile * (2 * TILE), pl.mat_b, bar);
+  if (pl.abs_b) bulk_g2s(stage + pl.abs, p.absidx + (size_t)tile * (pl.abs_b / 4), pl.abs_b, bar);
+}
+
+// Dynamic tile scheduler.  CTA b starts with tile b; further tiles are tickets gridDim.x + atomicAdd(next).  A
+// ticket is requested one iteration before its bulk copies are issued, so the atomic's latency is never waited
+// for.  The last CTA to finish zeroes both words for the next launch on the stream.
+__device__ __forceinline__ int sched_next(unsigned int* sched) { return (int)(gridDim.x + atomicAdd(sched, 1u)); }
+__device__ __forceinline__ void sched_done(unsigned int* sched) {
+  __threadfence();
+  if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
+    sched[0] = 0u;
+    sched[1] = 0u;
+    __threadfence();
+  }
+}
+
+template <int D, int ND, int NFP, int TILE>
+__device__ __forceinline__ void load_geom(const StageParams& p, const StagePlan& pl, const unsigned char* stage,
+                                          const double* gtab, int lane, FaceGeom<D, ND, NFP, TILE>& g) {
+  constexpr int NF = D + 1;
   if (p.geoidx != nullptr) {
-    const double* gt = p.geotab + (size_t)p.geoidx[(size_t)tile * TILE + lane] * (D * D);
+    const int cls = reinterpret_cast<const uint16_t*>(stage + pl.geo)[lane];
+    const double* gt = (p.nclass <= GEO_SMEM_CLASSES) ? gtab + cls * (D * D) : p.geotab + (size_t)cls * (D * D);
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
-      for (int k = 0; k < D; ++k) g.ji[r][k] = __ldg(gt + r * D + k);
+      for (int k = 0; k < D; ++k) g.ji[r][k] = gt[r * D + k];
   } else {
-    const double* geo = p.geo + (size_t)tile * (D * D * TILE) + lane;
+    const double* geo = reinterpret_cast<const double*>(stage + pl.geo) + lane;
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
       for (int k = 0; k < D; ++k) g.ji[r][k] = geo[(r * D + k) * TILE];
   }
-  const int32_t* nb = p.nbr + (size_t)tile * (NF * TILE) + lane;
-  const uint8_t* cd = p.code + (size_t)tile * (NF * TILE) + lane;
+  const int32_t* nb = reinterpret_cast<const int32_t*>(stage + pl.nbr) + lane;
+  const uint8_t* cd = stage + pl.code + lane;
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
     g.nb[f] = nb[f * TILE];
     g.cd[f] = cd[f * TILE];
   }
-  mbar_wait(bar, 0);
 }
+
+// CTA-wide setup shared by both kernels: barriers, facet node table, geometry class table
+template <int NS, int NTHREADS>
+__device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan& pl, unsigned char* smem,
+                                          const unsigned char* ftab, int ftab_size, int dd) {
+  const int tid = threadIdx.x;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < ftab_size; i += NTHREADS) smem[pl.ftab + i] = ftab[i];
+  if (p.geoidx != nullptr && p.nclass <= GEO_SMEM_CLASSES) {
+    double* gt = reinterpret_cast<double*>(smem + pl.gtab);
+    for (int i = tid; i < p.nclass * dd; i += NTHREADS) gt[i] = p.geotab[i];
+  }
+  __syncthreads();
+}
+
+// Producer prologue / per-iteration step (thread 0 only).  slot_tile[s] = tile held or being filled by slot s.
+#define SG_PIPE_PROLOGUE(GT)                                                                               \
+  int* slot_tile = reinterpret_cast<int*>(smem + pl.bars + 8 * NS);                                        \
+  int t_ahead = 0;                                                                                         \
+  if (tid == 0) {                                                                                          \
+    int t = blockIdx.x;                                                                                    \
+    _Pragma("unroll") for (int s = 0; s < NS - 1; ++s) {                                                   \
+      slot_tile[s] = t;                                                                                    \
+      if (t < p.ntiles) issue_tile<D, ND, TILE, GT>(p, pl, smem + s * pl.stage_bytes, bars + s, p.tile0 + t); \
+      t = sched_next(p.sched);                                                                             \
+    }                                                                                                      \
+    t_ahead = t;                                                                                           \
+  }                                                                                                        \
+  if (NS == 1) __syncthreads();
+
+#define SG_PIPE_ADVANCE(GT)                                                                                \
+  if (tid == 0) {                                                                                          \
+    const int sn = (it + NS - 1) % NS;                                                                     \
+    slot_tile[sn] = t_ahead;                                                                               \
+    if (t_ahead < p.ntiles) {                                                                              \
+      issue_tile<D, ND, TILE, GT>(p, pl, smem + sn * pl.stage_bytes, bars + sn, p.tile0 + t_ahead);        \
+      t_ahead = sched_next(p.sched);                                                                       \
+    }                                                                                                      \
+  }                                                                                                        \
+  if (NS == 1) __syncthreads();
 
 // ---------------------------------------------------------------------------------------------
 // F-type pass:   out_i = Dv(in)_i - A_cell * absu_i            (K1, K5)
 //                out_i = c0*ax0_i + c1*ax1_i + c2*(Dv(in)_i - A_cell*absu_i)   (K3, AXPY)
+// Persistent CTAs with a dynamic tile scheduler; the bulk copies of the next NS-1 tiles are in flight while a
+// tile is computed.
 // ---------------------------------------------------------------------------------------------
-template <int D, int P, int TILE, int SPLIT, int MINB, bool AXPY>
+template <int D, int P, int TILE, int SPLIT, int MINB, int NS, bool AXPY, bool AXS>
 __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageParams p) {
   using E = ElemOps<D, P>;
-  constexpr int ND = E::ND, NFP = E::NFP, KS = D * D * ND, KU = D * ND, IPT = D / SPLIT;
+  constexpr int ND = E::ND, NFP = E::NFP, KU = D * ND, IPT = D / SPLIT, NT = TILE * SPLIT;
   static_assert(D % SPLIT == 0, "SPLIT must divide D");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sIn = reinterpret_cast<double*>(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sIn + KS * TILE);
-  unsigned char* sft = reinterpret_cast<unsigned char*>(bar + 2);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StagePlan pl = make_plan<D, ND, TILE, NS, false, (AXPY && AXS)>(p.geoidx != nullptr, false,
+                                                                        p.absidx != nullptr, E::FTAB_SIZE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
+  const unsigned char* sft = smem + pl.ftab;
+  const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
+  cta_setup<NS, NT>(p, pl, smem, E::ftab(), E::FTAB_SIZE, D * D);
 
-  const int lane = threadIdx.x % TILE, ig = threadIdx.x / TILE;
-  const int tile = p.tile0 + blockIdx.x;
-  FaceGeom<D, ND, NFP, TILE> g;
-  stage_prologue<D, ND, NFP, TILE, KS, (AXPY ? KU : 0), TILE * SPLIT, E::FTAB_SIZE>(p, tile, lane, sIn, bar, sft, E::ftab(), g);
+  const int tid = threadIdx.x, lane = tid % TILE, ig = tid / TILE;
+  SG_PIPE_PROLOGUE(false)
+  for (int it = 0;; ++it) {
+    const int slot = it % NS;
+    SG_PIPE_ADVANCE(false)
+    const int t = slot_tile[slot];
+    if (t >= p.ntiles) break;
+    const int tile = p.tile0 + t;
+    unsigned char* stage = smem + slot * pl.stage_bytes;
+    const double* sIn = reinterpret_cast<const double*>(stage + pl.in);
+    mbar_wait(bars + slot, (it / NS) & 1);
 
-  int aidx = -1;
-  if (p.absidx != nullptr) aidx = p.absidx[(size_t)tile * TILE + lane];
+    FaceGeom<D, ND, NFP, TILE> g;
+    load_geom<D, ND, NFP, TILE>(p, pl, stage, gtab, lane, g);
+    int aidx = -1;
+    if (pl.abs_b) aidx = reinterpret_cast<const int32_t*>(stage + pl.abs)[lane];
 
-  FCtx<D, ND, NFP, TILE> c;
-  c.tileS = sIn;
-  c.gIn = p.in;
-  c.sft = sft;
-  c.g = &g;
-  c.tile = tile;
+    FCtx<D, ND, NFP, TILE> c;
+    c.tileS = sIn;
+    c.gIn = p.in;
+    c.sft = sft;
+    c.g = &g;
+    c.tile = tile;
 #pragma unroll
-  for (int ii = 0; ii < IPT; ++ii) {
-    const int i = ig * IPT + ii;
-    c.rowoff = i * D * ND * TILE;
-    c.own = sIn + c.rowoff + lane;
-    double acc[ND];
+    for (int ii = 0; ii < IPT; ++ii) {
+      const int i = ig * IPT + ii;
+      c.rowoff = i * D * ND * TILE;
+      c.own = sIn + c.rowoff + lane;
+      double acc[ND];
 #pragma unroll
-    for (int a = 0; a < ND; ++a) acc[a] = 0.0;
-    E::volF(c, acc);
-    E::liftF(c, acc);
-    const size_t orow = ((size_t)tile * KU + i * ND) * TILE + lane;
-    if (aidx >= 0) {
-      // sponge: - Minv * int phi_a (sigma u_i)   (elastic.py:207-208), A precomputed per sponge cell
-      double ua[ND];
+      for (int a = 0; a < ND; ++a) acc[a] = 0.0;
+      E::volF(c, acc);
+      E::liftF(c, acc);
+      const size_t orow = ((size_t)tile * KU + i * ND) * TILE + lane;
+      if (aidx >= 0) {
+        // sponge: - Minv * int phi_a (sigma u_i)   (elastic.py:207-208), A precomputed per sponge cell
+        double ua[ND];
 #pragma unroll
-      for (int b = 0; b < ND; ++b) ua[b] = p.absu[orow + (size_t)b * TILE];
-      const double* A = p.absmat + aidx;
+        for (int b = 0; b < ND; ++b) ua[b] = p.absu[orow + (size_t)b * TILE];
+        const double* A = p.absmat + aidx;
 #pragma unroll
-      for (int a = 0; a < ND; ++a)
+        for (int a = 0; a < ND; ++a)
 #pragma unroll
-        for (int b = 0; b < ND; ++b) acc[a] = fma(-A[(size_t)(a * ND + b) * p.nabs_pad], ua[b], acc[a]);
+          for (int b = 0; b < ND; ++b) acc[a] = fma(-A[(size_t)(a * ND + b) * p.nabs_pad], ua[b], acc[a]);
+      }
+      if (AXPY && AXS) {
+        const double* a0 = reinterpret_cast<const double*>(stage + pl.ax0) + i * ND * TILE + lane;
+        const double* a1 = reinterpret_cast<const double*>(stage + pl.ax1) + i * ND * TILE + lane;
+#pragma unroll
+        for (int a = 0; a < ND; ++a)
+          p.out[orow + (size_t)a * TILE] = fma(p.c0, a0[a * TILE], fma(p.c1, a1[a * TILE], p.c2 * acc[a]));
+      } else {
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+          double v = acc[a];
+          if (AXPY) v = fma(p.c0, p.ax0[orow + (size_t)a * TILE], fma(p.c1, p.ax1[orow + (size_t)a * TILE], p.c2 * v));
+          p.out[orow + (size_t)a * TILE] = v;
+        }
+      }
     }
-#pragma unroll
-    for (int a = 0; a < ND; ++a) {
-      double v = acc[a];
-      if (AXPY) v = fma(p.c0, p.ax0[orow + (size_t)a * TILE], fma(p.c1, p.ax1[orow + (size_t)a * TILE], p.c2 * v));
-      p.out[orow + (size_t)a * TILE] = v;
-    }
+    __syncthreads();   // the stage may be refilled from the next iteration on
   }
+  if (tid == 0) sched_done(p.sched);
 }
 
 // ---------------------------------------------------------------------------------------------
-// G-type pass:   out_ij = lam*delta_ij*div + mu*(G_ij + G_ji),  G_ij = d~_j in_i      (K2, K4)
-//                out_ij = c0*ax0_ij + c1*ax1_ij + c2*(...)                           (K6, AXPY)
+// G-type pass:   out_ij = lam*delta_ij*div + mu*(G_ij + G_ji) [+ src],  G_ij = d~_j in_i      (K2, K4)
+//                out_ij = c0*ax0_ij + c1*ax1_ij + c2*(...)                                   (K6, AXPY)
+// XREG (only with SPLIT == 1): the gradients G_ij stay in registers instead of the shared X buffer.
 // ---------------------------------------------------------------------------------------------
-template <int D, int P, int TILE, int SPLIT, int MINB, bool AXPY>
+template <int D, int P, int TILE, int SPLIT, int MINB, int NS, bool AXPY, bool AXS, bool XREG>
 __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageParams p) {
   using E = ElemOps<D, P>;
-  constexpr int ND = E::ND, NFP = E::NFP, KS = D * D * ND, KU = D * ND, IPT = D / SPLIT;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sIn = reinterpret_cast<double*>(smem_raw);
-  double* sX = sIn + KU * TILE;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sX + KS * TILE);
-  unsigned char* sft = reinterpret_cast<unsigned char*>(bar + 2);
+  constexpr int ND = E::ND, NFP = E::NFP, KS = D * D * ND, IPT = D / SPLIT, NT = TILE * SPLIT;
+  static_assert(!XREG || SPLIT == 1, "register-resident gradients need one thread per cell");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StagePlan pl = make_plan<D, ND, TILE, NS, true, (AXPY && AXS), !XREG>(p.geoidx != nullptr, p.mat != nullptr,
+                                                                              false, E::FTAB_SIZE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
+  const unsigned char* sft = smem + pl.ftab;
+  const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
+  double* sX = reinterpret_cast<double*>(smem + pl.x);
+  cta_setup<NS, NT>(p, pl, smem, E::ftab(), E::FTAB_SIZE, D * D);
 
-  const int lane = threadIdx.x % TILE, ig = threadIdx.x / TILE;
-  const int tile = p.tile0 + blockIdx.x;
-  FaceGeom<D, ND, NFP, TILE> g;
-  stage_prologue<D, ND, NFP, TILE, KU, (AXPY ? KS : 0), TILE * SPLIT, E::FTAB_SIZE>(p, tile, lane, sIn, bar, sft, E::ftab(), g);
+  const int tid = threadIdx.x, lane = tid % TILE, ig = tid / TILE;
+  SG_PIPE_PROLOGUE(true)
+  for (int it = 0;; ++it) {
+    const int slot = it % NS;
+    SG_PIPE_ADVANCE(true)
+    const int t = slot_tile[slot];
+    if (t >= p.ntiles) break;
+    const int tile = p.tile0 + t;
+    // source entries of this tile: requested now, looked at after the tile has been computed and stored
+    int s_lo = 0, s_hi = 0;
+    if (p.src_start != nullptr) {
+      s_lo = p.src_start[tile];
+      s_hi = p.src_start[tile + 1];
+    }
+    unsigned char* stage = smem + slot * pl.stage_bytes;
+    const double* sIn = reinterpret_cast<const double*>(stage + pl.in);
+    mbar_wait(bars + slot, (it / NS) & 1);
 
-  GCtx<D, ND, NFP, TILE> c;
-  c.tileU = sIn;
-  c.gIn = p.in;
-  c.sft = sft;
-  c.g = &g;
-  c.tile = tile;
+    FaceGeom<D, ND, NFP, TILE> g;
+    load_geom<D, ND, NFP, TILE>(p, pl, stage, gtab, lane, g);
+
+    GCtx<D, ND, NFP, TILE> c;
+    c.tileU = sIn;
+    c.gIn = p.in;
+    c.sft = sft;
+    c.g = &g;
+    c.tile = tile;
+    double XR[XREG ? KS : 1];
 #pragma unroll
-  for (int ii = 0; ii < IPT; ++ii) {
-    const int i = ig * IPT + ii;
-    c.rowoff = i * ND * TILE;
-    c.own = sIn + c.rowoff + lane;
-    double R[D * ND];
+    for (int ii = 0; ii < IPT; ++ii) {
+      const int i = ig * IPT + ii;
+      c.rowoff = i * ND * TILE;
+      c.own = sIn + c.rowoff + lane;
+      double R[D * ND];
 #pragma unroll
-    for (int a = 0; a < D * ND; ++a) R[a] = 0.0;
-    E::volG(c, R);
-    E::liftG(c, R);
-    double* X = sX + (size_t)(i * D) * ND * TILE + lane;
+      for (int a = 0; a < D * ND; ++a) R[a] = 0.0;
+      E::volG(c, R);
+      E::liftG(c, R);
+      double* X = sX + (size_t)(i * D) * ND * TILE + lane;
 #pragma unroll
-    for (int j = 0; j < D; ++j)
+      for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+          double v = g.ji[0][j] * R[a];
+#pragma unroll
+          for (int r = 1; r < D; ++r) v = fma(g.ji[r][j], R[r * ND + a], v);
+          if (XREG)
+            XR[(i * D + j) * ND + a] = v;
+          else
+            X[(j * ND + a) * TILE] = v;
+        }
+    }
+    if (SPLIT > 1) __syncthreads();
+
+    double lam = p.lam_c, mu = p.mu_c;
+    if (pl.mat_b) {
+      const double* m = reinterpret_cast<const double*>(stage + pl.mat) + lane;
+      lam = m[0];
+      mu = m[TILE];
+    }
+    const double* X = sX + lane;
+    double* out = p.out + (size_t)tile * (KS * TILE);
+#pragma unroll
+    for (int ii = 0; ii < IPT; ++ii) {
+      const int i = ig * IPT + ii;
 #pragma unroll
       for (int a = 0; a < ND; ++a) {
-        double v = g.ji[0][j] * R[a];
+        double div = XREG ? XR[a] : X[(0 * ND + a) * TILE];
 #pragma unroll
-        for (int r = 1; r < D; ++r) v = fma(g.ji[r][j], R[r * ND + a], v);
-        X[(j * ND + a) * TILE] = v;
-      }
-  }
-  if (SPLIT > 1) __syncthreads();
-
-  double lam = p.lam_c, mu = p.mu_c;
-  if (p.lam != nullptr) {
-    lam = p.lam[(size_t)tile * TILE + lane];
-    mu = p.mu[(size_t)tile * TILE + lane];
-  }
-  const double* X = sX + lane;
+        for (int k = 1; k < D; ++k) div += XREG ? XR[(k * D + k) * ND + a] : X[((k * D + k) * ND + a) * TILE];
+        const double ld = lam * div;
 #pragma unroll
-  for (int ii = 0; ii < IPT; ++ii) {
-    const int i = ig * IPT + ii;
-#pragma unroll
-    for (int a = 0; a < ND; ++a) {
-      double div = X[(0 * ND + a) * TILE];
-#pragma unroll
-      for (int k = 1; k < D; ++k) div += X[((k * D + k) * ND + a) * TILE];
-      const double ld = lam * div;
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        double v = mu * (X[((i * D + j) * ND + a) * TILE] + X[((j * D + i) * ND + a) * TILE]);
-        if (j == i) v += ld;
-        const size_t o = ((size_t)tile * KS + (i * D + j) * ND + a) * TILE + lane;
-        if (AXPY) v = fma(p.c0, p.ax0[o], fma(p.c1, p.ax1[o], p.c2 * v));
-        p.out[o] = v;
+        for (int j = 0; j < D; ++j) {
+          double v = XREG ? mu * (XR[(i * D + j) * ND + a] + XR[(j * D + i) * ND + a])
+                          : mu * (X[((i * D + j) * ND + a) * TILE] + X[((j * D + i) * ND + a) * TILE]);
+          if (j == i) v += ld;
+          const int o = ((i * D + j) * ND + a) * TILE + lane;
+          if (AXPY && AXS) {
+            const double* a0 = reinterpret_cast<const double*>(stage + pl.ax0);
+            const double* a1 = reinterpret_cast<const double*>(stage + pl.ax1);
+            v = fma(p.c0, a0[o], fma(p.c1, a1[o], p.c2 * v));
+          } else if (AXPY) {
+            const size_t og = (size_t)tile * (KS * TILE) + o;
+            v = fma(p.c0, p.ax0[og], fma(p.c1, p.ax1[og], p.c2 * v));
+          }
+          out[o] = v;
+        }
       }
     }
+    __syncthreads();   // stage and X free again; this tile's stores are ordered before the source update below
+    if (s_hi > s_lo) {
+      const int64_t st = *p.step;
+      if (st >= 0 && st < p.nsteps)
+        for (int k = s_lo + tid; k < s_hi; k += NT) out[p.src_off[k]] += p.src_scale * p.amp[st * p.nsrc + k];
+    }
   }
+  if (tid == 0) sched_done(p.sched);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,17 +576,7 @@ __global__ void relayout_kernel(double* __restrict__ dev, double* __restrict__ h
   }
 }
 
-// stress += scale * amp[step][k] at the listed device addresses (elastic.py:149-154, 285-288)
-__global__ void add_source_kernel(double* __restrict__ s, const int64_t* __restrict__ addr,
-                                  const double* __restrict__ amp, const int64_t* __restrict__ step, int64_t nsteps,
-                                  int64_t nsrc, double scale, int64_t addr_lo, int64_t addr_hi) {
-  const int64_t st = *step;
-  if (st < 0 || st >= nsteps) return;
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nsrc; k += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t a = addr[k];
-    if (a >= addr_lo && a < addr_hi) s[a] += scale * amp[st * nsrc + k];
-  }
-}
+// device-side step counter: indexes the source table so that the step graph replays without host arguments
 __global__ void bump_step_kernel(int64_t* step) { *step += 1; }
 __global__ void set_step_kernel(int64_t* step, int64_t v) { *step = v; }
 
