@@ -74,17 +74,14 @@ const std::vector<Variant>& variants() {
       // first entry of each (dim, degree) is the default; the others are tuning candidates selectable with
       // SG_TILE / SG_SPLIT / SG_MINB / SG_NS (scripts/perf_probe.py)
       //            D  P  TILE SPLIT MINB MINBA NSP NSA AXS   XREG
-      make_variant<2, 1, 64, 1, 8, 4, 2, 2, true, true>(),
-      make_variant<2, 1, 64, 1, 10, 4, 2, 2, true, true>(),
       make_variant<2, 1, 128, 1, 4, 2, 2, 2, true, true>(),
+      make_variant<2, 1, 64, 1, 8, 4, 2, 2, true, true>(),
       make_variant<2, 2, 64, 1, 8, 3, 2, 2, true, true>(),
       make_variant<2, 2, 64, 1, 10, 3, 2, 2, true, true>(),
-      make_variant<2, 2, 64, 1, 8, 3, 3, 2, true, true>(),
-      make_variant<2, 2, 64, 1, 6, 3, 3, 2, true, false>(),
       make_variant<2, 2, 128, 1, 4, 2, 2, 2, true, true>(),
       make_variant<2, 2, 64, 2, 4, 3, 2, 2, true, false>(),
-      make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>(),
       make_variant<2, 3, 32, 1, 8, 4, 2, 2, true, true>(),
+      make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>(),
       make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>(),
       make_variant<3, 1, 64, 1, 4, 3, 2, 2, true, false>(),
       make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>(),

@@ -337,7 +337,7 @@ __device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan&
     }                                                                                                      \
     t_ahead = t;                                                                                           \
   }                                                                                                        \
-  if (NS == 1) __syncthreads();
+  __syncthreads();   /* slot_tile[0 .. NS-2] visible to every warp */
 
 #define SG_PIPE_ADVANCE(GT)                                                                                \
   if (tid == 0) {                                                                                          \
