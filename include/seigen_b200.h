@@ -97,6 +97,13 @@ int sg_set_state(sg_solver* h, const double* u, const double* s);
 int sg_get_state(sg_solver* h, double* u, double* s);
 int sg_get_field(sg_solver* h, int which, double* out);
 
+/* Receivers: the sensors tests/explosive_source/uy.py:36-43 probes in the VTU output ((45,149), (90,149), (140,149)).
+ * Receiver k sits in owned cell cell[k] with basis values weights[k][nd] at its position; after every time step
+ * sg_step records u at the receivers on the device.  sg_get_receivers copies steps [first_step, first_step+nsteps)
+ * as out[step][k][dim].  n = 0 clears. */
+int sg_set_receivers(sg_solver* h, int64_t n, const int64_t* cell, const double* weights, int64_t max_steps);
+int sg_get_receivers(sg_solver* h, int64_t first_step, int64_t nsteps, double* out);
+
 /* The loop body of ElasticLF4.run (elastic.py:283-304) `nsteps` times, starting at 0-based step index
  * `first_step` (only used to index the source table).  Work is queued on the solver's stream; the call
  * returns without waiting (sg_get_state / sg_synchronize wait). */

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "sg_synchronize": (C.c_int, [_P]),
     "sg_last_step_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "sg_mark": (C.c_int, [_P, C.c_int]),
+    "sg_set_receivers": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64]),
+    "sg_get_receivers": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "sg_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int64]),
     "sg_time_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "sg_set_halo_plan": (C.c_int, [_P, C.c_int64, _P]),

@@ -143,6 +143,9 @@ struct sg_solver {
   DevBuf<uint8_t> code;
   DevBuf<int64_t> step_dev, send_cells;
   DevBuf<int32_t> src_start, src_off;
+  DevBuf<int64_t> rec_cell;               // receivers: owning cell, basis weights, samples [max_steps][nrec][dim]
+  DevBuf<double> rec_w, rec_data;
+  int64_t nrec = 0, rec_steps = 0;
   DevBuf<unsigned int> sched;             // [3 parts][2] dynamic tile scheduler words (sg::sched_next)
   int nsm = 148;
   int occ[4] = {0, 0, 0, 0};            // resident CTAs per SM of f_plain, f_axpy, g_plain, g_axpy
@@ -554,6 +557,7 @@ void sg_destroy(sg_solver* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->rec_cell.release(); h->rec_w.release(); h->rec_data.release();
   h->sched.release(); h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->comm) cudaStreamDestroy(h->comm);
@@ -751,7 +755,10 @@ int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
       rc = enqueue_step_peers(h, dt);
     else
       for (int k = 1; k <= 6 && rc == SG_OK; ++k) rc = launch_stage(h, k, SG_PART_ALL, dt, st);
-    if (rc == SG_OK && h->nsrc > 0) sg::bump_step_kernel<<<1, 1, 0, st>>>(h->step_dev.p);
+    if (rc == SG_OK && h->nrec > 0)
+      sg::receivers_kernel<<<1, 128, 0, st>>>(h->u.p, h->rec_cell.p, h->rec_w.p, h->rec_data.p, h->step_dev.p,
+                                              h->rec_steps, (int)h->nrec, h->nd, h->dim, h->tile);
+    if (rc == SG_OK && (h->nsrc > 0 || h->nrec > 0)) sg::bump_step_kernel<<<1, 1, 0, st>>>(h->step_dev.p);
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc != SG_OK) {
       if (g) cudaGraphDestroy(g);
@@ -767,7 +774,7 @@ int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
     h->graph_dt = dt;
     h->graph_version = h->config_version;
   }
-  if (h->nsrc > 0) {
+  if (h->nsrc > 0 || h->nrec > 0) {
     sg::set_step_kernel<<<1, 1, 0, st>>>(h->step_dev.p, first_step);
     SG_CUDA(cudaGetLastError());
   }
@@ -801,6 +808,44 @@ int sg_synchronize(sg_solver* h) {
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->stream));
   SG_CUDA(cudaStreamSynchronize(h->comm));
+  return SG_OK;
+}
+
+int sg_set_receivers(sg_solver* h, int64_t n, const int64_t* cell, const double* weights, int64_t max_steps) {
+  if (!h) return fail(SG_EINVAL, "null solver");
+  if (n < 0 || max_steps < 0 || (n > 0 && (!cell || !weights))) return fail(SG_EINVAL, "sg_set_receivers: bad arguments");
+  SG_CUDA(cudaSetDevice(h->device));
+  SG_CUDA(cudaStreamSynchronize(h->stream));
+  if (n == 0 && h->nrec == 0) return SG_OK;
+  h->config_version++;
+  h->nrec = 0;
+  h->rec_steps = 0;
+  if (n == 0 || max_steps == 0) return SG_OK;
+  std::vector<int64_t> c((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    if (cell[k] < 0 || cell[k] >= h->n_owned) return fail(SG_EINVAL, "sg_set_receivers: cell is not owned");
+    c[(size_t)k] = cell[k];
+  }
+  SG_CUDA(h->rec_cell.alloc((size_t)n));
+  SG_CUDA(h->rec_w.alloc((size_t)n * h->nd));
+  SG_CUDA(h->rec_data.alloc((size_t)max_steps * n * h->dim));
+  SG_CUDA(cudaMemcpy(h->rec_cell.p, c.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemcpy(h->rec_w.p, weights, (size_t)n * h->nd * 8, cudaMemcpyHostToDevice));
+  SG_CUDA(cudaMemset(h->rec_data.p, 0, (size_t)max_steps * n * h->dim * 8));
+  h->nrec = n;
+  h->rec_steps = max_steps;
+  return SG_OK;
+}
+
+int sg_get_receivers(sg_solver* h, int64_t first_step, int64_t nsteps, double* out) {
+  if (!h || !out) return fail(SG_EINVAL, "sg_get_receivers: null argument");
+  if (first_step < 0 || nsteps < 0 || first_step + nsteps > h->rec_steps)
+    return fail(SG_EINVAL, "sg_get_receivers: step range outside the recorded window");
+  SG_CUDA(cudaSetDevice(h->device));
+  const size_t row = (size_t)h->nrec * h->dim;
+  SG_CUDA(cudaMemcpyAsync(out, h->rec_data.p + (size_t)first_step * row, (size_t)nsteps * row * 8,
+                          cudaMemcpyDeviceToHost, h->stream));
+  SG_CUDA(cudaStreamSynchronize(h->stream));
   return SG_OK;
 }
 

@@ -578,6 +578,24 @@ __global__ void relayout_kernel(double* __restrict__ dev, double* __restrict__ h
 
 // device-side step counter: indexes the source table so that the step graph replays without host arguments
 __global__ void bump_step_kernel(int64_t* step) { *step += 1; }
+
+// receivers (the sensors of tests/explosive_source/uy.py:36-43): velocity at fixed points, sampled after every step.
+// rec[step][r][comp] = sum_a w[r][a] * u[cell_r, a, comp];  one thread per (receiver, component)
+__global__ void receivers_kernel(const double* __restrict__ u, const int64_t* __restrict__ cell,
+                                 const double* __restrict__ w, double* __restrict__ rec,
+                                 const int64_t* __restrict__ step, int64_t max_steps, int n, int nd, int d, int tile) {
+  const int64_t st = *step;
+  if (st < 0 || st >= max_steps) return;
+  const int K = nd * d;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * d; idx += gridDim.x * blockDim.x) {
+    const int r = idx / d, comp = idx % d;
+    const int64_t e = cell[r];
+    const double* base = u + ((e / tile) * K + comp * nd) * tile + e % tile;
+    double acc = 0.0;
+    for (int a = 0; a < nd; ++a) acc = fma(w[r * nd + a], base[(int64_t)a * tile], acc);
+    rec[(st * n + r) * d + comp] = acc;
+  }
+}
 __global__ void set_step_kernel(int64_t* step, int64_t v) { *step = v; }
 
 // halo pack / unpack: whole cells, K rows each; buffer is [cell][k]

@@ -74,6 +74,11 @@ class ElasticLF4(object):
             self.absorption_function = None
             self.source_function = None
             self.source_expression = None
+            #: optional sensor positions [(x, y[, z]), ...]: after run(), ``receiver_data[step, k, :]`` holds the
+            #: velocity at receiver k after every time step (what tests/explosive_source/uy.py:36-43 extracts from
+            #: the per-step VTU files); NaN for receivers outside this rank's cells
+            self.receivers = None
+            self.receiver_data = None
             self.density = None
             self.dt = None
             self.mu = None
@@ -184,6 +189,7 @@ class ExplicitElasticLF4(ElasticLF4):
                 check(lib.sg_set_material(dev.handle, float(self.density), float(lam), float(mu), None, None))
             self._upload_absorption()
             self._upload_source(times or [])
+            self._upload_receivers(len(times or []))
 
     def _upload_absorption(self):
         dev = self._dev
@@ -248,6 +254,45 @@ class ExplicitElasticLF4(ElasticLF4):
             self.source_function.dat.data[...] = 0.0
             self.source_function.dat.data.reshape(-1)[sdof] = amp[-1]
             self._source_key = key
+
+    def _upload_receivers(self, nsteps):
+        dev = self._dev
+        self._rec_local = None
+        if not self.receivers or nsteps == 0:
+            check(lib.sg_set_receivers(dev.handle, 0, None, None, 0))
+            return
+        mesh, el = self.mesh, self.S.elem
+        v = mesh.coords[mesh.cells[self.S.cell_order]]                     # (n_owned, d+1, d)
+        J = np.swapaxes(v[:, 1:] - v[:, :1], 1, 2)
+        Jinv = np.linalg.inv(J)
+        cells, weights, which = [], [], []
+        for k, pt in enumerate(self.receivers):
+            xi = np.einsum("erk,ek->er", Jinv, np.asarray(pt, dtype=float)[None] - v[:, 0])
+            ok = np.flatnonzero((xi >= -1e-10).all(axis=1) & (xi.sum(axis=1) <= 1 + 1e-10))
+            if len(ok):
+                cells.append(int(ok[0]))
+                weights.append(el.tabulate(xi[ok[0]][None])[0])
+                which.append(k)
+        self._rec_local = (np.array(which, dtype=np.int64), nsteps)
+        if not cells:
+            check(lib.sg_set_receivers(dev.handle, 0, None, None, 0))
+            return
+        c = np.ascontiguousarray(cells, dtype=np.int64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        check(lib.sg_set_receivers(dev.handle, len(c), ptr(c), ptr(w), nsteps))
+
+    def _download_receivers(self):
+        if self._rec_local is None:
+            self.receiver_data = None
+            return
+        which, nsteps = self._rec_local
+        d = self.dimension
+        out = np.full((nsteps, len(self.receivers), d), np.nan)
+        if len(which):
+            buf = np.empty((nsteps, len(which), d))
+            check(lib.sg_get_receivers(self._dev.handle, 0, nsteps, ptr(buf)))
+            out[:, which] = buf
+        self.receiver_data = out
 
     # -- state transfer ------------------------------------------------------------------------------------------
     def _upload_state(self):
@@ -321,6 +366,7 @@ class ExplicitElasticLF4(ElasticLF4):
                 self._advance(len(times), 0)
                 self._download_state()
             dev.synchronize()
+            self._download_receivers()
         self.steps_done = len(times)
         if len(times) and not self.output:
             self.last_run_ms = dev.last_step_ms()

@@ -1,0 +1,133 @@
+"""The reference's scenarios through the public API on the GPU (mirrors of tests/eigenmode/eigenmode_2d.py,
+eigenmode_3d.py and tests/explosive_source/explosive_source_lf4.py written against ``from seigen_b200 import *``),
+checked against the CPU oracle on the same mesh, degree, dt and source: relative L2 error <= 1e-10 per field
+(BASELINE.json's tolerance; also tests/tiling/explosive_source.py:659-660), the eigenmode errors / rates, and the
+REF-C1 sensor trace."""
+import numpy as np
+import pytest
+
+from tests.scenarios import (EXPL_LAM, EXPL_MU, LAM, MU, eigenmode_dt, eigenmode_expressions, explosive_dt,
+                             explosive_expressions, explosive_oracle, locate, rates)
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class EigenmodeLF4:
+    """tests/eigenmode/eigenmode_2d.py:7-65 / eigenmode_3d.py:7-69 with the firedrake import swapped."""
+
+    def __init__(self, dim, N, degree, dt, solver='explicit', output=False):
+        from seigen_b200 import ElasticLF4, UnitCubeMesh, UnitSquareMesh
+        self.dim = dim
+        self.mesh = UnitSquareMesh(N, N) if dim == 2 else UnitCubeMesh(N, N, N)
+        self.elastic = ElasticLF4.create(self.mesh, "DG", degree, dimension=dim, solver=solver, output=output)
+        self.elastic.density = 1.0
+        self.elastic.dt = dt
+        self.elastic.mu = MU
+        self.elastic.l = LAM
+
+    def run(self, T=5.0):
+        from seigen_b200 import Function
+        el = self.elastic
+        uic, sic = eigenmode_expressions(self.dim, el.dt, 0, el.dt / 2.0)
+        el.u0.assign(Function(el.U).interpolate(uic))
+        el.s0.assign(Function(el.S).interpolate(sic))
+        return el.run(T)
+
+    def error(self, u1, s1):
+        from seigen_b200 import errornorm_l2
+        uex, sex = eigenmode_expressions(self.dim, self.elastic.dt, 5, 5 + self.elastic.dt / 2.0)
+        return errornorm_l2(u1, uex), errornorm_l2(s1, sex)
+
+
+def oracle_eigenmode(dim, N, p):
+    from tests.test_oracle_eigenmode import run_eigenmode
+    return run_eigenmode(dim, N, p)
+
+
+@pytest.mark.parametrize("dim,p,Ns", [(2, 1, (4, 8, 16)), (2, 2, (4, 8)), (2, 3, (4, 8)), (2, 4, (4,)),
+                                      (3, 1, (2, 4)), (3, 2, (2, 4)), (3, 3, (2,))])
+def test_eigenmode_errors_and_rates(dim, p, Ns):
+    errs = []
+    for N in Ns:
+        em = EigenmodeLF4(dim, N, p, eigenmode_dt(N, p))
+        u1, s1 = em.run()
+        eu, es = em.error(u1, s1)
+        if (dim, p) in ((2, 1), (2, 2), (2, 3), (3, 1)) or N == 2:
+            n, eu_o, es_o = oracle_eigenmode(dim, N, p)
+            assert em.elastic.steps_done == n
+            assert eu == pytest.approx(eu_o, rel=1e-6) and es == pytest.approx(es_o, rel=1e-6)
+        errs.append((eu, es))
+    if len(Ns) > 1:
+        hs = [1.0 / N for N in Ns]
+        ru, rs = rates([e[0] for e in errs], hs)[-1], rates([e[1] for e in errs], hs)[-1]
+        # central flux: u ~ p+1, s ~ p asymptotically; coarse meshes are pre-asymptotic
+        assert ru > (p + 1) - 0.9 and rs > p - 0.35, (errs, ru, rs)
+
+
+def _explosive_gpu(Lx, Ly, h, T, receivers):
+    from seigen_b200 import ElasticLF4, Function, FunctionSpace, RectangleMesh
+    mesh = RectangleMesh(int(Lx / h), int(Ly / h), Lx, Ly)
+    el = ElasticLF4.create(mesh, "DG", 2, dimension=2, solver="explicit", output=False)
+    el.density, el.mu, el.l = 1.0, EXPL_MU, EXPL_LAM
+    el.dt = explosive_dt(h)
+    source, sponge = explosive_expressions(Lx, Ly)
+    el.source_expression = source
+    el.source_function = Function(el.S)
+    el.source = el.source_expression
+    el.absorption_function = Function(FunctionSpace(mesh, "DG", 4))
+    el.absorption = sponge
+    el.receivers = receivers
+    u1, s1 = el.run(T)
+    return el, u1, s1
+
+
+def test_explosive_source_1000_steps_parity_and_ref_c1():
+    from oracle.c_oracle import COracle
+    from oracle.elastic_oracle import step_times
+    from tests.test_oracle_refc import compare_with_ref
+    Lx, Ly, h = 100.0, 50.0, 2.5
+    dt = explosive_dt(h)
+    T = 1000.5 * dt
+    el, u1, s1 = _explosive_gpu(Lx, Ly, h, T, [(45.0, Ly - 1.0), (90.0, Ly - 1.0)])
+    assert el.steps_done == 1000
+
+    mesh, orc, src = explosive_oracle(Lx, Ly, h)
+    co = COracle(orc)
+    u = np.zeros((orc.E, orc.nd, 2))
+    s = np.zeros((orc.E, orc.nd, 2, 2))
+    e, xi = locate(mesh.coords, mesh.cells, (45.0, Ly - 1.0))
+    phi = orc.el.tab(xi[None])[0]
+    times = step_times(T, dt)
+    trace = []
+    for t in times:
+        co.step_inplace(u, s, src(t), dt)
+        trace.append(phi @ u[e])
+    trace = np.array(trace)
+    order = el.S.cell_order
+    assert rel_err(u1.dat.data.reshape(orc.E, orc.nd, 2), u[order]) < 1e-10
+    assert rel_err(s1.dat.data.reshape(orc.E, orc.nd, 2, 2), s[order]) < 1e-10
+    # device-side receivers == oracle trace, and both track the reference's external solution
+    rec = el.receiver_data
+    assert rec.shape == (1000, 2, 2) and np.isfinite(rec).all()
+    assert rel_err(rec[:, 0], trace) < 1e-9
+    w = np.array(times) <= 0.45
+    rel, peak_ratio, dt_peak = compare_with_ref(np.array(times)[w], -rec[w, 0, 1])
+    assert rel < 0.25 and 0.8 < peak_ratio < 1.2 and abs(dt_peak) < 0.01
+
+
+def test_run_twice_continues_and_output_mode(tmp_path, monkeypatch):
+    """run(T) twice == run(2T) without source (u0 <- u1, s0 <- s1 after each run, elastic.py:296, 304); output=True
+    writes one snapshot per step plus the initial one (elastic.py:273, 310)."""
+    monkeypatch.chdir(tmp_path)
+    a = EigenmodeLF4(2, 4, 2, eigenmode_dt(4, 2))
+    ua, sa = a.run(T=1.0)
+    ua = ua.dat.data.copy()
+    b = EigenmodeLF4(2, 4, 2, eigenmode_dt(4, 2), output=True)
+    b.run(T=0.5)
+    n1 = b.elastic.steps_done
+    ub, sb = b.elastic.run(0.5)
+    assert n1 + b.elastic.steps_done == a.elastic.steps_done
+    assert rel_err(ub.dat.data, ua) < 1e-12
+    assert np.array_equal(b.elastic.u0.dat.data, ub.dat.data)
+    assert len(list(tmp_path.glob("velocity_*.vtk"))) == 2 * (n1 + 1)
