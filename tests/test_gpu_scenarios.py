@@ -40,9 +40,12 @@ class EigenmodeLF4:
         return errornorm_l2(u1, uex), errornorm_l2(s1, sex)
 
 
+MIN_RATES = {(2, 1): (1.5, 0.9), (2, 2): (2.8, 2.2), (2, 3): (3.7, 2.7), (3, 1): (0.8, 1.0), (3, 2): (3.0, 2.2)}
+
+
 def oracle_eigenmode(dim, N, p):
     from tests.test_oracle_eigenmode import run_eigenmode
-    return run_eigenmode(dim, N, p)
+    return run_eigenmode(dim, N, p, fields=True)
 
 
 @pytest.mark.parametrize("dim,p,Ns", [(2, 1, (4, 8, 16)), (2, 2, (4, 8)), (2, 3, (4, 8)), (2, 4, (4,)),
@@ -54,15 +57,21 @@ def test_eigenmode_errors_and_rates(dim, p, Ns):
         u1, s1 = em.run()
         eu, es = em.error(u1, s1)
         if (dim, p) in ((2, 1), (2, 2), (2, 3), (3, 1)) or N == 2:
-            n, eu_o, es_o = oracle_eigenmode(dim, N, p)
+            n, eu_o, es_o, u_o, s_o = oracle_eigenmode(dim, N, p)
             assert em.elastic.steps_done == n
-            assert eu == pytest.approx(eu_o, rel=1e-6) and es == pytest.approx(es_o, rel=1e-6)
+            order = em.elastic.S.cell_order
+            assert rel_err(u1.dat.data.reshape(u_o.shape), u_o[order]) < 1e-10
+            assert rel_err(s1.dat.data.reshape(s_o.shape), s_o[order]) < 1e-10
+            # (the two error norms use different quadrature rules for the non-polynomial exact solution)
+            assert eu == pytest.approx(eu_o, rel=2e-3) and es == pytest.approx(es_o, rel=2e-3)
         errs.append((eu, es))
     if len(Ns) > 1:
         hs = [1.0 / N for N in Ns]
         ru, rs = rates([e[0] for e in errs], hs)[-1], rates([e[1] for e in errs], hs)[-1]
-        # central flux: u ~ p+1, s ~ p asymptotically; coarse meshes are pre-asymptotic
-        assert ru > (p + 1) - 0.9 and rs > p - 0.35, (errs, ru, rs)
+        # central flux: u ~ p+1, s ~ p asymptotically; N = 2 -> 4 in 3D is
+        # pre-asymptotic (Appendix C: P1 u 4.75e-1 -> 2.55e-1)
+        ru_min, rs_min = MIN_RATES[(dim, p)]
+        assert ru > ru_min and rs > rs_min, (errs, ru, rs)
 
 
 def _explosive_gpu(Lx, Ly, h, T, receivers):
@@ -89,14 +98,14 @@ def test_explosive_source_1000_steps_parity_and_ref_c1():
     Lx, Ly, h = 100.0, 50.0, 2.5
     dt = explosive_dt(h)
     T = 1000.5 * dt
-    el, u1, s1 = _explosive_gpu(Lx, Ly, h, T, [(45.0, Ly - 1.0), (90.0, Ly - 1.0)])
+    el, u1, s1 = _explosive_gpu(Lx, Ly, h, T, [(45.3, Ly - 1.0), (45.0, Ly - 1.0)])
     assert el.steps_done == 1000
 
     mesh, orc, src = explosive_oracle(Lx, Ly, h)
     co = COracle(orc)
     u = np.zeros((orc.E, orc.nd, 2))
     s = np.zeros((orc.E, orc.nd, 2, 2))
-    e, xi = locate(mesh.coords, mesh.cells, (45.0, Ly - 1.0))
+    e, xi = locate(mesh.coords, mesh.cells, (45.3, Ly - 1.0))      # strictly inside a cell: DG values are unique there
     phi = orc.el.tab(xi[None])[0]
     times = step_times(T, dt)
     trace = []
@@ -112,7 +121,7 @@ def test_explosive_source_1000_steps_parity_and_ref_c1():
     assert rec.shape == (1000, 2, 2) and np.isfinite(rec).all()
     assert rel_err(rec[:, 0], trace) < 1e-9
     w = np.array(times) <= 0.45
-    rel, peak_ratio, dt_peak = compare_with_ref(np.array(times)[w], -rec[w, 0, 1])
+    rel, peak_ratio, dt_peak = compare_with_ref(np.array(times)[w], -rec[w, 1, 1])     # sensor C1 = (45, 149)
     assert rel < 0.25 and 0.8 < peak_ratio < 1.2 and abs(dt_peak) < 0.01
 
 

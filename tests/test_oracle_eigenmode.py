@@ -11,7 +11,7 @@ from seigen_b200.mesh import UnitCubeMesh, UnitSquareMesh
 from tests.scenarios import LAM, MU, eigenmode_dt, eigenmode_expressions, rates
 
 
-def run_eigenmode(dim, N, p, T=5.0):
+def run_eigenmode(dim, N, p, T=5.0, fields=False):
     mesh = UnitSquareMesh(N, N) if dim == 2 else UnitCubeMesh(N, N, N)
     orc = ElasticOracle(mesh.coords, mesh.cells, p)
     orc.l, orc.mu, orc.density = LAM, MU, 1.0
@@ -25,7 +25,7 @@ def run_eigenmode(dim, N, p, T=5.0):
     uex, sex = eigenmode_expressions(dim, dt, 5.0, 5.0 + dt / 2.0)       # t = 5 hard-coded, eigenmode_2d.py:42, 46
     eu = orc.l2_error(u, lambda xq: uex.evaluate(xq.reshape(-1, dim)).reshape(xq.shape[:2] + (dim,)))
     es = orc.l2_error(s, lambda xq: sex.evaluate(xq.reshape(-1, dim)).reshape(xq.shape[:2] + (dim, dim)))
-    return n, eu, es
+    return (n, eu, es, u, s) if fields else (n, eu, es)
 
 
 EXPECTED_2D = {   # (p, N): (steps, u_err, s_err)   SURVEY.md Appendix C
