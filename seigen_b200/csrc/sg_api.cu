@@ -163,7 +163,7 @@ struct sg_solver {
   DevBuf<int32_t> send_peer;                 // [nsend] index into the peer tables
   DevBuf<double*> rfield;                    // [4][npeers] peers' u, s, uh, sh
   DevBuf<unsigned long long*> rflag;         // [npeers] my flag slot in each peer's ctl
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_int[6] = {}, ev_bnd[6] = {};
   // CUDA graph of one time step
   cudaGraphExec_t graph = nullptr;
   double graph_dt = 0.0;
@@ -319,23 +319,32 @@ int enqueue_exchange(sg_solver* h, int which, cudaStream_t st) {
 
 const int STAGE_OUTPUT[7] = {-1, SG_FIELD_UH, SG_FIELD_SH, SG_FIELD_U, SG_FIELD_SH, SG_FIELD_UH, SG_FIELD_S};
 
-// One time step on a rank with peers.  Per pass the (few) cut-adjacent tiles run on the comm stream, followed by
-// push -> signal -> wait, while the interior tiles run concurrently on the compute stream; the two branches join
-// before the next pass.  Both branches read the previous pass's output and write disjoint cells.
+// One time step on a rank with peers: two chains that only meet where the data says they must.
+//   compute stream:  interior(1) -> interior(2) -> ... -> interior(6)
+//   comm stream:     boundary(1) -> push/signal/wait -> boundary(2) -> push/signal/wait -> ...
+// interior(k+1) needs boundary(k) (it reads cut-adjacent neighbours) but never the halo, so the exchange latency is
+// off its critical path; boundary(k+1) needs the halo rows (wait) and interior(k).  Each kernel of pass k+1 waits
+// for both kernels of pass k, which also orders every write-after-read on the recycled scratch fields.
 int enqueue_step_peers(sg_solver* h, double dt) {
   cudaStream_t st = h->stream, cm = h->comm;
+  SG_CUDA(cudaEventRecord(h->ev_fork, st));
+  SG_CUDA(cudaStreamWaitEvent(cm, h->ev_fork, 0));
   for (int k = 1; k <= 6; ++k) {
-    SG_CUDA(cudaEventRecord(h->ev_fork, st));
-    SG_CUDA(cudaStreamWaitEvent(cm, h->ev_fork, 0));
+    if (k > 1) {
+      SG_CUDA(cudaStreamWaitEvent(cm, h->ev_int[k - 2], 0));   // boundary(k) after interior(k-1)
+      SG_CUDA(cudaStreamWaitEvent(st, h->ev_bnd[k - 2], 0));   // interior(k) after boundary(k-1)
+    }
     int rc = launch_stage(h, k, SG_PART_BOUNDARY, dt, cm);
     if (rc) return rc;
+    SG_CUDA(cudaEventRecord(h->ev_bnd[k - 1], cm));
     rc = enqueue_exchange(h, STAGE_OUTPUT[k], cm);
     if (rc) return rc;
     rc = launch_stage(h, k, SG_PART_INTERIOR, dt, st);
     if (rc) return rc;
-    SG_CUDA(cudaEventRecord(h->ev_join, cm));
-    SG_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    SG_CUDA(cudaEventRecord(h->ev_int[k - 1], st));
   }
+  SG_CUDA(cudaEventRecord(h->ev_join, cm));
+  SG_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   return SG_OK;
 }
 
@@ -426,6 +435,10 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  for (int k = 0; k < 6; ++k) {
+    SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_int[k], cudaEventDisableTiming));
+    SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_bnd[k], cudaEventDisableTiming));
+  }
   SG_CUDA_H(h->sched.alloc(8));
   SG_CUDA_H(cudaMemsetAsync(h->sched.p, 0, 8 * sizeof(unsigned int), h->stream));
   SG_CUDA_H(h->ctl.alloc(sg::SG_CTL_WORDS));
@@ -556,6 +569,10 @@ void sg_destroy(sg_solver* h) {
   if (h->ev_sync) cudaEventDestroy(h->ev_sync);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int k = 0; k < 6; ++k) {
+    if (h->ev_int[k]) cudaEventDestroy(h->ev_int[k]);
+    if (h->ev_bnd[k]) cudaEventDestroy(h->ev_bnd[k]);
+  }
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   h->rec_cell.release(); h->rec_w.release(); h->rec_data.release();
   h->sched.release(); h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
