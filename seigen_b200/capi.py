@@ -14,7 +14,7 @@ import numpy as np
 __all__ = ["lib", "load", "SgError", "MeshDesc", "LIB_PATH", "check", "pinned_zeros", "PeerDesc",
            "FIELD_U", "FIELD_S", "FIELD_UH", "FIELD_SH", "PART_ALL", "PART_BOUNDARY", "PART_INTERIOR"]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libseigen_b200.so")
+LIB_PATH = os.environ.get("SG_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libseigen_b200.so")
 
 FIELD_U, FIELD_S, FIELD_UH, FIELD_SH = 0, 1, 2, 3
 PART_ALL, PART_BOUNDARY, PART_INTERIOR = 0, 1, 2
