@@ -2,13 +2,12 @@
 # sweep kernel variants on the GPU box (development aid)
 run() { env "$@" python scripts/perf_probe.py $ARGS --reps 1 | tail -1; }
 ARGS="--degree 2"
-run SG_TILE=64 SG_SPLIT=1 SG_MINB=8 SG_NS=22; run SG_TILE=64 SG_SPLIT=1 SG_MINB=10 SG_NS=22; run SG_TILE=64 SG_SPLIT=1 SG_MINB=8 SG_NS=32; run SG_TILE=64 SG_SPLIT=1 SG_MINB=6 SG_NS=32; run SG_TILE=128; run SG_TILE=64 SG_SPLIT=2
-run SG_TILE=64 SG_SPLIT=1 SG_MINB=8 SG_NS=22 SG_GRID_PER_SM=4; run SG_TILE=64 SG_SPLIT=1 SG_MINB=8 SG_NS=22 SG_GRID_PER_SM=16
+run SG_TILE=64 SG_PF=1; run SG_TILE=64 SG_PF=0; run SG_TILE=128 SG_PF=1
 ARGS="--degree 1"
-run SG_TILE=64 SG_MINB=8; run SG_TILE=64 SG_MINB=10; run SG_TILE=128
+run SG_TILE=128 SG_PF=1; run SG_TILE=128 SG_PF=0; run SG_TILE=64
 ARGS="--dim 3 --degree 1 --nx 128 --ny 32 --nz 32"
-run SG_TILE=64; run SG_TILE=32 SG_SPLIT=1; run SG_TILE=32 SG_SPLIT=3
-ARGS="--degree 3 --nx 1000 --ny 400"; run SG_TILE=64; run SG_TILE=32
-ARGS="--degree 4 --nx 800 --ny 300"; run A=1
-ARGS="--dim 3 --degree 2 --nx 64 --ny 32 --nz 32"; run A=1
-ARGS="--dim 3 --degree 3 --nx 64 --ny 32 --nz 16"; run A=1
+run SG_TILE=64 SG_PF=1; run SG_TILE=64 SG_PF=0; run SG_TILE=32 SG_SPLIT=3
+ARGS="--degree 3 --nx 1000 --ny 400"; run SG_PF=1; run SG_PF=0
+ARGS="--degree 4 --nx 800 --ny 300"; run SG_PF=1; run SG_PF=0
+ARGS="--dim 3 --degree 2 --nx 64 --ny 32 --nz 32"; run SG_PF=1; run SG_PF=0
+ARGS="--dim 3 --degree 3 --nx 64 --ny 32 --nz 16"; run SG_PF=1; run SG_PF=0
