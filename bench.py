@@ -276,11 +276,11 @@ def run_gpu(args):
     ms_local = dev.last_step_ms()
     ms = max_over_ranks(ms_local)
     value = ndof * K / (ms * 1e-3)
-    nsrc_kernels = 4 if el.source_function is not None else 0
+    step_counter = 1 if el.source_function is not None else 0     # the source is added inside the G-type passes
     if world == 1:
-        launches = K * (6 + nsrc_kernels)                      # 6 passes (+3 source adds +1 step counter)
-    else:                                                      # per pass: boundary, interior, push, signal, wait
-        launches = K * (6 * 5 + (7 if nsrc_kernels else 0))
+        launches = K * (6 + step_counter)                         # six fused passes (+ device-side step counter)
+    else:                                                         # per pass: boundary, interior, push, signal, wait
+        launches = K * (6 * 5 + step_counter)
 
     # ---- per-pass timing of the six kernels (roofline of the dominant one) ----------------------------------
     reps = max(10, min(K, 50))

@@ -29,7 +29,7 @@ import numpy as np
 from .refelem import RefElem, facet_perms, get_refelem
 
 __all__ = ["Mesh", "Topology", "IntervalMesh", "UnitIntervalMesh", "RectangleMesh", "UnitSquareMesh",
-           "BoxMesh", "UnitCubeMesh", "BOUNDARY", "build_topology", "perturb_vertices"]
+           "BoxMesh", "UnitCubeMesh", "BOUNDARY", "build_topology", "perturb_vertices", "read_gmsh", "write_gmsh"]
 
 BOUNDARY = 0x80
 
@@ -58,9 +58,14 @@ class _Comm:
 
 
 class Mesh:
-    """A conforming simplicial mesh given by explicit ``(coords, cells)`` arrays."""
+    """A conforming simplicial mesh given by explicit ``(coords, cells)`` arrays, or read from a Gmsh ``.msh`` file
+    (``Mesh(mesh_file)`` as in tests/tiling/explosive_source.py:531-532, for meshes made from
+    tests/explosive_source/src/domain.geo)."""
 
-    def __init__(self, coords, cells, name="mesh"):
+    def __init__(self, coords, cells=None, name="mesh", dim=None):
+        if isinstance(coords, (str, bytes)) or hasattr(coords, "__fspath__"):
+            name = str(coords)
+            coords, cells = read_gmsh(coords, dim=dim)
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         if coords.ndim == 1:
             coords = coords[:, None]
@@ -203,6 +208,94 @@ def build_topology(coords: np.ndarray, cells: np.ndarray) -> Topology:
         raise ValueError("degenerate cell (zero volume)")
     jinv = np.linalg.inv(J)                              # jinv[e, r, k]
     return Topology(nbr, code, np.ascontiguousarray(jinv), detj)
+
+
+def read_gmsh(path, dim=None):
+    """(coords, cells) of the highest-dimensional simplices in a Gmsh ASCII mesh (format 2.2 or 4.1).
+
+    Lower-dimensional elements (the ``Physical Line`` tags of domain.geo) are ignored: every boundary is a free
+    surface in ElasticLF4.  For planar meshes the constant z coordinate is dropped."""
+    with open(path) as fh:
+        lines = [ln.strip() for ln in fh]
+    sect = {}
+    i = 0
+    while i < len(lines):
+        if lines[i].startswith("$") and not lines[i].startswith("$End"):
+            name = lines[i][1:]
+            j = i + 1
+            while not lines[j].startswith("$End"):
+                j += 1
+            sect[name] = lines[i + 1:j]
+            i = j
+        i += 1
+    if "MeshFormat" not in sect:
+        raise ValueError(f"{path}: not a Gmsh ASCII mesh")
+    version, ftype = sect["MeshFormat"][0].split()[:2]
+    if ftype != "0":
+        raise ValueError(f"{path}: binary Gmsh files are not supported")
+    simplex = {2: 3, 4: 4}                                  # Gmsh element type -> vertices (3-node triangle, 4-node tet)
+    tags, pts, elems = [], [], {2: [], 4: []}
+    if version.startswith("2"):
+        n = int(sect["Nodes"][0])
+        for ln in sect["Nodes"][1:n + 1]:
+            t = ln.split()
+            tags.append(int(t[0]))
+            pts.append([float(x) for x in t[1:4]])
+        m = int(sect["Elements"][0])
+        for ln in sect["Elements"][1:m + 1]:
+            t = ln.split()
+            et, ntag = int(t[1]), int(t[2])
+            if et in simplex:
+                elems[et].append([int(x) for x in t[3 + ntag:3 + ntag + simplex[et]]])
+    elif version.startswith("4"):
+        body = sect["Nodes"]
+        nblocks = int(body[0].split()[0])
+        k = 1
+        for _ in range(nblocks):
+            nn = int(body[k].split()[3])
+            k += 1
+            tags += [int(x) for x in body[k:k + nn]]
+            pts += [[float(x) for x in ln.split()[:3]] for ln in body[k + nn:k + 2 * nn]]
+            k += 2 * nn
+        body = sect["Elements"]
+        nblocks = int(body[0].split()[0])
+        k = 1
+        for _ in range(nblocks):
+            _, _, et, ne = (int(x) for x in body[k].split())
+            k += 1
+            if et in simplex:
+                elems[et] += [[int(x) for x in ln.split()[1:1 + simplex[et]]] for ln in body[k:k + ne]]
+            k += ne
+    else:
+        raise ValueError(f"{path}: unsupported Gmsh format version {version}")
+    et = 4 if (elems[4] and dim != 2) else 2
+    if not elems[et]:
+        raise ValueError(f"{path}: no triangles or tetrahedra found")
+    pts = np.array(pts, dtype=np.float64)
+    lut = np.full(max(tags) + 1, -1, dtype=np.int64)
+    lut[np.array(tags)] = np.arange(len(tags))
+    cells = lut[np.array(elems[et], dtype=np.int64)]
+    used = np.unique(cells)                                  # drop nodes no cell refers to
+    renum = np.full(len(pts), -1, dtype=np.int64)
+    renum[used] = np.arange(len(used))
+    d = 3 if et == 4 else 2
+    return pts[used][:, :d], renum[cells].astype(np.int32)
+
+
+def write_gmsh(path, coords, cells):
+    """Gmsh 2.2 ASCII writer (triangles / tetrahedra); the counterpart of read_gmsh for fixtures and exports."""
+    coords = np.asarray(coords, dtype=np.float64)
+    cells = np.asarray(cells)
+    et = {3: 2, 4: 4}[cells.shape[1]]
+    with open(path, "w") as fh:
+        fh.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(coords))
+        for i, x in enumerate(coords):
+            xyz = list(x) + [0.0] * (3 - len(x))
+            fh.write("%d %.17g %.17g %.17g\n" % (i + 1, *xyz))
+        fh.write("$EndNodes\n$Elements\n%d\n" % len(cells))
+        for i, c in enumerate(cells):
+            fh.write("%d %d 2 10 6 %s\n" % (i + 1, et, " ".join(str(int(v) + 1) for v in c)))
+        fh.write("$EndElements\n")
 
 
 # ----------------------------------------------------------------------------
