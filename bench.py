@@ -146,7 +146,8 @@ def marmousi_problem(nranks, scale=1.0):
     el.source = el.source_expression
     rng = np.random.default_rng(1234 + el.S.plan.rank)
     el.u0.dat.data[...] = 1e-3 * rng.standard_normal(el.u0.dat.data.shape)
-    el.s0.dat.data[...] = 1e-3 * rng.standard_normal(el.s0.dat.data.shape)
+    s0 = 1e-3 * rng.standard_normal(el.s0.dat.data.shape)
+    el.s0.dat.data[...] = 0.5 * (s0 + np.swapaxes(s0, 1, 2))      # a stress tensor: symmetric
     name = f"marmousi_2d_p{DEGREE}_{nx}x{ny}_per_gpu"
     return el, name
 
@@ -348,6 +349,8 @@ def run_gpu(args):
                           "dof_per_gpu": int(ndof_local), "dof_total": int(ndof), "dt": dt,
                           "material": "per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1",
                           "source": "Ricker, one cell box per tile", "sponge": "none",
+                          "initial_data": "random 1e-3 velocity, random 1e-3 symmetric stress",
+                          "stress_storage": "symmetric (upper triangle)" if dev.symmetric else "full",
                           "l2": "state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)" % (8e-6 * ndof_local),
                           "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass, exchange={el.halo_mode}",
                           "setup_s": t_setup},

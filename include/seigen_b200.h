@@ -30,6 +30,7 @@ extern "C" {
 #define SG_EINVAL (-1)   /* bad argument / unsupported (dim, degree) */
 #define SG_ECUDA (-2)    /* a CUDA runtime call failed */
 #define SG_ESTATE (-3)   /* call made in the wrong state (e.g. stepping before materials are set) */
+#define SG_EASYM (-4)    /* asymmetric stress / source handed to a solver created with symmetric_stress = 1 */
 
 #define SG_BOUNDARY 0x80 /* bit 7 of a facet code marks an exterior facet */
 
@@ -54,7 +55,13 @@ typedef struct sg_mesh_desc {
   int32_t geom_classes; /* 1: cells whose Jinv agree to 2^-36 relative (translates of one another on uniform
                            meshes) share one geometry record, saving dim*dim*8 B of HBM traffic per cell per
                            pass; falls back to per-cell geometry above 4096 classes.  0: always per cell */
-  int32_t reserved;
+  int32_t symmetric_stress; /* 1: keep only the upper triangle of every stress field on the device.  The stress RHS
+                           g (elastic.py:211-219) is symmetric by construction, so if s0 and the source are symmetric
+                           every stress of the run is, bit for bit, and the step moves 1/6 (2D) to 1/4 (3D) fewer
+                           bytes.  The boundary still carries all dim*dim components (TensorFunctionSpace,
+                           elastic.py:81); sg_set_state / sg_set_source return SG_EASYM if the premise fails and
+                           the caller re-creates the solver with 0 (what seigen_b200/elastic.py does).  0: store all
+                           dim*dim components, no premise */
 } sg_mesh_desc;
 
 /* Which device field sg_get_field / sg_field_ptr address. */

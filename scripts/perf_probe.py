@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--nz", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--sym", type=int, default=1, help="symmetric stress storage on the device")
     a = ap.parse_args()
     t0 = time.time()
     if a.dim == 2:
@@ -30,12 +31,14 @@ def main():
     E = mesh.num_cells()
     d = a.dim
     ndof = E * el.nd * (d + d * d)
-    dev = DeviceSolver(mesh, a.degree)
+    dev = DeviceSolver(mesh, a.degree, symmetric=bool(a.sym))
     t1 = time.time()
     dev.set_material(1.0, 0.5, 0.25)
     rng = np.random.default_rng(0)
     u = rng.standard_normal((E * el.nd, d)) * 1e-3
     s = rng.standard_normal((E * el.nd, d, d)) * 1e-3
+    if a.sym:
+        s = 0.5 * (s + np.swapaxes(s, 1, 2))
     dev.set_state(u, s)
     dt = 1e-6
     dev.step(3, dt)
@@ -45,7 +48,7 @@ def main():
         ms = dev.last_step_ms() / a.steps
         import os
         tag = " ".join(f"{k}={os.environ[k]}" for k in ("SG_TILE", "SG_SPLIT", "SG_MINB") if k in os.environ)
-        print(f"{tag} dim={d} p={a.degree} cells={E} dof={ndof} setup={t1 - t0:.1f}s  {ms:.4f} ms/step  "
+        print(f"{tag} sym={a.sym} dim={d} p={a.degree} cells={E} dof={ndof} setup={t1 - t0:.1f}s  {ms:.4f} ms/step  "
               f"{ndof / ms / 1e6:.2f} Gupd/s  {64 * ndof / ms / 1e6:.0f} GB/s algorithmic")
     dev.close()
 

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-__all__ = ["lib", "load", "SgError", "MeshDesc", "LIB_PATH", "check", "pinned_zeros", "PeerDesc",
+__all__ = ["lib", "load", "SgError", "SgAsymmetric", "MeshDesc", "LIB_PATH", "check", "pinned_zeros", "PeerDesc",
            "FIELD_U", "FIELD_S", "FIELD_UH", "FIELD_SH", "PART_ALL", "PART_BOUNDARY", "PART_INTERIOR"]
 
 LIB_PATH = os.environ.get("SG_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libseigen_b200.so")
@@ -21,7 +21,16 @@ PART_ALL, PART_BOUNDARY, PART_INTERIOR = 0, 1, 2
 
 
 class SgError(RuntimeError):
-    pass
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
+
+
+class SgAsymmetric(SgError):
+    """SG_EASYM: asymmetric stress / source handed to a solver created with ``symmetric_stress = 1``."""
+
+
+EASYM = -4
 
 
 class MeshDesc(C.Structure):
@@ -36,7 +45,7 @@ class MeshDesc(C.Structure):
         ("device", C.c_int32),
         ("n_boundary", C.c_int32),
         ("geom_classes", C.c_int32),
-        ("reserved", C.c_int32),
+        ("symmetric_stress", C.c_int32),
     ]
 
 
@@ -123,7 +132,8 @@ lib = _Lazy()
 def check(rc: int):
     if rc != 0:
         msg = load().sg_last_error()
-        raise SgError(f"seigen_b200 error {rc}: {msg.decode() if msg else '?'}")
+        cls = SgAsymmetric if rc == EASYM else SgError
+        raise cls(f"seigen_b200 error {rc}: {msg.decode() if msg else '?'}", rc)
 
 
 def pinned_zeros(shape):

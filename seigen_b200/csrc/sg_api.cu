@@ -31,19 +31,34 @@ int fail(int code, const std::string& msg) {
 // ---- per-element kernel configuration ------------------------------------------------------
 struct Variant {
   int dim, degree, nd, nfp, tile, split, minb, ns_plain, ns_axpy, axs;
-  sg::StagePlan (*plan_f)(bool classes, bool mat, bool sponge);
-  sg::StagePlan (*plan_f_axpy)(bool classes, bool mat, bool sponge);
-  sg::StagePlan (*plan_g)(bool classes, bool mat, bool sponge);
-  sg::StagePlan (*plan_g_axpy)(bool classes, bool mat, bool sponge);
-  const void* f_plain;
-  const void* f_axpy;
-  const void* g_plain;
-  const void* g_axpy;
+  // [0]: full stress storage (D*D components), [1]: symmetric storage (upper triangle)
+  sg::StagePlan (*plan_f[2])(bool classes, bool mat, bool sponge);
+  sg::StagePlan (*plan_f_axpy[2])(bool classes, bool mat, bool sponge);
+  sg::StagePlan (*plan_g[2])(bool classes, bool mat, bool sponge);
+  sg::StagePlan (*plan_g_axpy[2])(bool classes, bool mat, bool sponge);
+  const void* f_plain[2];
+  const void* f_axpy[2];
+  const void* g_plain[2];
+  const void* g_axpy[2];
 };
 
 // TILE cells per tile, SPLIT threads per cell, MINB / MINBA CTAs per SM the compiler must allow for the plain / AXPY
 // kernels (register cap), NSP / NSA pipeline depth of the plain / AXPY kernels, AXS: stage the AXPY operands through
 // shared memory (bulk copies) instead of reading them from L2, XREG: G-type gradients in registers (SPLIT == 1)
+template <int D, int P, int TILE, int SPLIT, int MINB, int MINBA, int NSP, int NSA, bool AXS, bool XREG, bool SYM>
+void fill_variant(Variant& v) {
+  using E = ElemOps<D, P>;
+  constexpr int m = SYM ? 1 : 0;
+  v.plan_f[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, false, false, false, SYM>(c, mt, sp, E::FTAB_SIZE); };
+  v.plan_f_axpy[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, false, AXS, false, SYM>(c, mt, sp, E::FTAB_SIZE); };
+  v.plan_g[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, true, false, !XREG, SYM>(c, mt, sp, E::FTAB_SIZE); };
+  v.plan_g_axpy[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, true, AXS, !XREG, SYM>(c, mt, sp, E::FTAB_SIZE); };
+  v.f_plain[m] = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false, SYM>;
+  v.f_axpy[m] = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS, SYM>;
+  v.g_plain[m] = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false, XREG, SYM>;
+  v.g_axpy[m] = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS, XREG, SYM>;
+}
+
 template <int D, int P, int TILE, int SPLIT, int MINB, int MINBA, int NSP, int NSA, bool AXS, bool XREG>
 Variant make_variant() {
   using E = ElemOps<D, P>;
@@ -58,14 +73,8 @@ Variant make_variant() {
   v.ns_plain = NSP;
   v.ns_axpy = NSA;
   v.axs = AXS;
-  v.plan_f = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, false, false>(c, m, sp, E::FTAB_SIZE); };
-  v.plan_f_axpy = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, false, AXS>(c, m, sp, E::FTAB_SIZE); };
-  v.plan_g = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, true, false, !XREG>(c, m, sp, E::FTAB_SIZE); };
-  v.plan_g_axpy = [](bool c, bool m, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, true, AXS, !XREG>(c, m, sp, E::FTAB_SIZE); };
-  v.f_plain = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false>;
-  v.f_axpy = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS>;
-  v.g_plain = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false, XREG>;
-  v.g_axpy = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS, XREG>;
+  fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, false>(v);
+  fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, true>(v);
   return v;
 }
 
@@ -84,10 +93,19 @@ const std::vector<Variant>& variants() {
       make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>(),
       make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>(),
       make_variant<3, 1, 64, 1, 4, 3, 2, 2, true, false>(),
+      make_variant<3, 1, 64, 1, 8, 4, 2, 2, true, false>(),
+      make_variant<3, 1, 64, 1, 6, 3, 2, 2, true, false>(),
+      make_variant<3, 1, 128, 1, 4, 2, 2, 2, true, false>(),
       make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>(),
       make_variant<3, 1, 32, 3, 4, 4, 3, 2, true, false>(),
+      make_variant<3, 1, 64, 3, 4, 3, 2, 2, true, false>(),
       make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>(),
+      make_variant<3, 2, 32, 3, 4, 4, 2, 2, true, false>(),
+      make_variant<3, 2, 32, 3, 5, 4, 2, 2, true, false>(),
+      make_variant<3, 2, 64, 3, 2, 2, 2, 1, true, false>(),
       make_variant<3, 3, 32, 3, 2, 2, 2, 1, false, false>(),
+      make_variant<3, 3, 32, 3, 3, 3, 2, 1, false, false>(),
+      make_variant<3, 3, 32, 3, 4, 3, 1, 1, false, false>(),
   };
   return v;
 }
@@ -132,7 +150,9 @@ template <class T> struct DevBuf {
 struct sg_solver {
   const Variant* var = nullptr;
   int dim = 0, degree = 0, nd = 0, nf = 0, tile = 0, device = 0;
-  int KU = 0, KS = 0;
+  int KU = 0, KS = 0;               // device rows per cell of a velocity / stress field
+  int sym = 0, ncs = 0, KS_full = 0; // symmetric stress storage; stored stress components; nd*dim*dim
+  DevBuf<unsigned int> asym;         // raised by the relayout kernel when a stress field handed in is not symmetric
   int64_t n_owned = 0, n_total = 0, n_owned_pad = 0, n_halo = 0, n_dev = 0, n_boundary = 0;
   int tiles_owned = 0, tiles_total = 0, tiles_boundary = 0;
   DevBuf<double> u, s, uh, sh;          // state + scratch, tile-blocked
@@ -228,29 +248,29 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
   switch (stage) {
     case 1:  // uh1 = Dv(s0) - P(sigma, u0)                         elastic.py:157-161, 292
       p.in = h->s.p; p.out = h->uh.p; p.absu = h->u.p;
-      fn = v->f_plain; pl = v->plan_f(classes, mat, sponge); occ = &h->occ[0];
+      fn = v->f_plain[h->sym]; pl = v->plan_f[h->sym](classes, mat, sponge); occ = &h->occ[0];
       break;
     case 2:  // stemp = Ds(uh1) + src                               elastic.py:163-167, 293
       p.in = h->uh.p; p.out = h->sh.p; p.src_scale = 1.0; gtype = true;
-      fn = v->g_plain; pl = v->plan_g(classes, mat, sponge); occ = &h->occ[2];
+      fn = v->g_plain[h->sym]; pl = v->plan_g[h->sym](classes, mat, sponge); occ = &h->occ[2];
       break;
     case 3:  // u1 = rho*u0 + dt*uh1 + dt^3/24*(Dv(stemp) - P(sigma, u0))   elastic.py:169-173, 341-345, 294-296
       p.in = h->sh.p; p.out = h->u.p; p.ax0 = h->u.p; p.ax1 = h->uh.p; p.absu = h->u.p;
       p.c0 = h->density; p.c1 = dt; p.c2 = c3;
-      fn = v->f_axpy; pl = v->plan_f_axpy(classes, mat, sponge); occ = &h->occ[1];
+      fn = v->f_axpy[h->sym]; pl = v->plan_f_axpy[h->sym](classes, mat, sponge); occ = &h->occ[1];
       break;
     case 4:  // sh1 = Ds(u1) + src                                  elastic.py:181-185, 300
       p.in = h->u.p; p.out = h->sh.p; p.src_scale = 1.0; gtype = true;
-      fn = v->g_plain; pl = v->plan_g(classes, mat, sponge); occ = &h->occ[2];
+      fn = v->g_plain[h->sym]; pl = v->plan_g[h->sym](classes, mat, sponge); occ = &h->occ[2];
       break;
     case 5:  // utemp = Dv(sh1) - P(sigma, u1)                      elastic.py:187-191, 301
       p.in = h->sh.p; p.out = h->uh.p; p.absu = h->u.p;
-      fn = v->f_plain; pl = v->plan_f(classes, mat, sponge); occ = &h->occ[0];
+      fn = v->f_plain[h->sym]; pl = v->plan_f[h->sym](classes, mat, sponge); occ = &h->occ[0];
       break;
     case 6:  // s1 = s0 + dt*sh1 + dt^3/24*(Ds(utemp) + src)        elastic.py:193-197, 348-352, 302-304
       p.in = h->uh.p; p.out = h->s.p; p.ax0 = h->s.p; p.ax1 = h->sh.p;
       p.c0 = 1.0; p.c1 = dt; p.c2 = c3; p.src_scale = c3; gtype = true;
-      fn = v->g_axpy; pl = v->plan_g_axpy(classes, mat, sponge); occ = &h->occ[3];
+      fn = v->g_axpy[h->sym]; pl = v->plan_g_axpy[h->sym](classes, mat, sponge); occ = &h->occ[3];
       break;
     default:
       return fail(SG_EINVAL, "sg_stage: stage must be 1..6");
@@ -287,20 +307,23 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
 
 int relayout(sg_solver* h, double* dev, double* host_order, int ncomp, bool to_device, cudaStream_t st,
              int64_t ncell) {
+  // ncomp: components at the boundary; stress fields of a symmetric-storage solver are packed on the device
   const int64_t total = ncell * h->nd * ncomp;
   if (total == 0) return SG_OK;
+  const int symd = (h->sym && ncomp == h->dim * h->dim) ? h->dim : 0;
   if (to_device)
-    sg::relayout_kernel<true><<<grid_for(total), 256, 0, st>>>(dev, host_order, ncell, h->n_owned,
-                                                               h->n_owned_pad, h->nd, ncomp, h->tile);
+    sg::relayout_kernel<true><<<grid_for(total), 256, 0, st>>>(dev, host_order, ncell, h->n_owned, h->n_owned_pad,
+                                                               h->nd, ncomp, h->tile, symd, h->asym.p);
   else
-    sg::relayout_kernel<false><<<grid_for(total), 256, 0, st>>>(dev, host_order, ncell, h->n_owned,
-                                                                h->n_owned_pad, h->nd, ncomp, h->tile);
+    sg::relayout_kernel<false><<<grid_for(total), 256, 0, st>>>(dev, host_order, ncell, h->n_owned, h->n_owned_pad,
+                                                                h->nd, ncomp, h->tile, symd, h->asym.p);
   SG_CUDA(cudaGetLastError());
   return SG_OK;
 }
 
 DevBuf<double>* field_buf(sg_solver* h, int which);
 int field_ncomp(sg_solver* h, int which);
+int field_ncomp_boundary(sg_solver* h, int which);
 
 // push my cut-adjacent cells of field `which` into the peers' halo tiles, publish, then wait for the peers' rows
 int enqueue_exchange(sg_solver* h, int which, cudaStream_t st) {
@@ -357,7 +380,11 @@ DevBuf<double>* field_buf(sg_solver* h, int which) {
   }
   return nullptr;
 }
+// components stored on the device / crossing the boundary
 int field_ncomp(sg_solver* h, int which) {
+  return (which == SG_FIELD_U || which == SG_FIELD_UH) ? h->dim : h->ncs;
+}
+int field_ncomp_boundary(sg_solver* h, int which) {
   return (which == SG_FIELD_U || which == SG_FIELD_UH) ? h->dim : h->dim * h->dim;
 }
 
@@ -398,8 +425,11 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   h->nf = v->dim + 1;
   h->tile = v->tile;
   h->device = d->device;
+  h->sym = d->symmetric_stress ? 1 : 0;
+  h->ncs = h->sym ? v->dim * (v->dim + 1) / 2 : v->dim * v->dim;
   h->KU = v->dim * v->nd;
-  h->KS = v->dim * v->dim * v->nd;
+  h->KS = h->ncs * v->nd;
+  h->KS_full = v->dim * v->dim * v->nd;
   h->n_owned = d->n_owned;
   h->n_total = d->n_total;
   h->n_halo = d->n_total - d->n_owned;
@@ -444,7 +474,10 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   SG_CUDA_H(h->ctl.alloc(sg::SG_CTL_WORDS));
   SG_CUDA_H(cudaMemsetAsync(h->ctl.p, 0, sg::SG_CTL_WORDS * 8, h->stream));
 
-  const size_t nU = (size_t)h->n_dev * h->KU, nS = (size_t)h->n_dev * h->KS;
+  SG_CUDA_H(h->asym.alloc(1));
+  SG_CUDA_H(cudaMemsetAsync(h->asym.p, 0, sizeof(unsigned int), h->stream));
+  // stress buffers are sized for full storage either way: they double as staging buffers for the boundary layout
+  const size_t nU = (size_t)h->n_dev * h->KU, nS = (size_t)h->n_dev * h->KS_full;
   SG_CUDA_H(h->u.alloc(nU));
   SG_CUDA_H(h->uh.alloc(nU));
   SG_CUDA_H(h->s.alloc(nS));
@@ -575,6 +608,7 @@ void sg_destroy(sg_solver* h) {
   }
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   h->rec_cell.release(); h->rec_w.release(); h->rec_data.release();
+  h->asym.release();
   h->sched.release(); h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->comm) cudaStreamDestroy(h->comm);
@@ -655,7 +689,7 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
   h->nsrc = 0;
   h->src_steps = 0;
   if (nsrc == 0 || nsteps == 0) return SG_OK;
-  const int dd = h->dim * h->dim;
+  const int dd = h->dim * h->dim, D = h->dim;
   // entries sorted by tile: the G-type CTA that produces a tile adds that tile's source values (src_start/src_off)
   std::vector<std::pair<int64_t, int64_t>> key((size_t)nsrc);   // (tile * tile_elems + offset, original column)
   const int64_t tile_elems = (int64_t)h->KS * h->tile;
@@ -664,19 +698,55 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
     const int64_t cell = dof / ((int64_t)h->nd * dd);
     if (dof < 0 || cell >= h->n_owned) return fail(SG_EINVAL, "sg_set_source: dof outside owned cells");
     const int r = (int)(dof % ((int64_t)h->nd * dd));
-    const int node = r / dd, comp = r % dd;
+    const int node = r / dd;
+    int comp = r % dd;
+    if (h->sym) {
+      const int i = comp / D, j = comp % D, a = i < j ? i : j, b = i < j ? j : i;
+      comp = a * D - a * (a - 1) / 2 + (b - a);
+    }
     key[(size_t)k] = {(cell / h->tile) * tile_elems + (int64_t)(comp * h->nd + node) * h->tile + cell % h->tile, k};
   }
   std::sort(key.begin(), key.end());
-  for (int64_t k = 1; k < nsrc; ++k)
-    if (key[(size_t)k].first == key[(size_t)k - 1].first) return fail(SG_EINVAL, "sg_set_source: duplicate dof");
+  if (h->sym) {
+    // (i,j) and (j,i) land on the same packed entry: they must carry the same values at every step (a zero entry
+    // may be left out by the caller), then one of them is kept
+    std::vector<std::pair<int64_t, int64_t>> uniq;
+    for (int64_t k = 0; k < nsrc;) {
+      int64_t e = k + 1;
+      while (e < nsrc && key[(size_t)e].first == key[(size_t)k].first) ++e;
+      const int r0 = (int)(sdof[key[(size_t)k].second] % ((int64_t)h->nd * dd)) % dd;
+      const bool offdiag = r0 / D != r0 % D;
+      bool ok = (e - k) == (offdiag ? 2 : 1);
+      if (ok && offdiag) {
+        const int64_t c0 = key[(size_t)k].second, c1 = key[(size_t)k + 1].second;
+        ok = sdof[c0] != sdof[c1];
+        for (int64_t n = 0; n < nsteps && ok; ++n) ok = amp[(size_t)(n * nsrc + c0)] == amp[(size_t)(n * nsrc + c1)];
+      } else if (!ok && offdiag && e - k == 1) {
+        // a lone off-diagonal entry is symmetric only if it is zero throughout
+        ok = true;
+        for (int64_t n = 0; n < nsteps && ok; ++n) ok = amp[(size_t)(n * nsrc + key[(size_t)k].second)] == 0.0;
+      }
+      if (!ok)
+        return fail(e - k > 2 ? SG_EINVAL : SG_EASYM,
+                    "sg_set_source: the source is not symmetric (or lists a dof twice) but the solver was created "
+                    "with symmetric_stress = 1");
+      uniq.push_back(key[(size_t)k]);
+      k = e;
+    }
+    key.swap(uniq);
+  } else {
+    for (int64_t k = 1; k < nsrc; ++k)
+      if (key[(size_t)k].first == key[(size_t)k - 1].first) return fail(SG_EINVAL, "sg_set_source: duplicate dof");
+  }
+  const int64_t ncol = nsrc;          // columns of the caller's table
+  nsrc = (int64_t)key.size();         // entries kept on the device
   std::vector<int32_t> start((size_t)h->tiles_owned + 1, 0), off((size_t)nsrc);
   std::vector<double> a((size_t)nsrc * nsteps);
   for (int64_t k = 0; k < nsrc; ++k) {
     const int64_t t = key[(size_t)k].first / tile_elems;
     start[(size_t)t + 1]++;
     off[(size_t)k] = (int32_t)(key[(size_t)k].first % tile_elems);
-    for (int64_t n = 0; n < nsteps; ++n) a[(size_t)(n * nsrc + k)] = amp[(size_t)(n * nsrc + key[(size_t)k].second)];
+    for (int64_t n = 0; n < nsteps; ++n) a[(size_t)(n * nsrc + k)] = amp[(size_t)(n * ncol + key[(size_t)k].second)];
   }
   for (size_t t = 0; t < (size_t)h->tiles_owned; ++t) start[t + 1] += start[t];
   SG_CUDA(h->src_start.alloc(start.size()));
@@ -700,11 +770,19 @@ int sg_set_state(sg_solver* h, const double* u, const double* s) {
     if (rc) return rc;
   }
   if (s) {
-    SG_CUDA(cudaMemcpyAsync(h->sh.p, s, (size_t)h->n_owned * h->KS * 8, cudaMemcpyHostToDevice, h->stream));
+    SG_CUDA(cudaMemcpyAsync(h->sh.p, s, (size_t)h->n_owned * h->KS_full * 8, cudaMemcpyHostToDevice, h->stream));
     int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, true, h->stream, h->n_owned);
     if (rc) return rc;
   }
+  unsigned int asym = 0;
+  if (s && h->sym) {
+    SG_CUDA(cudaMemcpyAsync(&asym, h->asym.p, sizeof(asym), cudaMemcpyDeviceToHost, h->stream));
+    SG_CUDA(cudaMemsetAsync(h->asym.p, 0, sizeof(asym), h->stream));
+  }
   SG_CUDA(cudaStreamSynchronize(h->stream));
+  if (asym)
+    return fail(SG_EASYM, "sg_set_state: the stress handed in is not symmetric but the solver was created with "
+                          "symmetric_stress = 1; create it with symmetric_stress = 0");
   return SG_OK;
 }
 
@@ -721,7 +799,7 @@ int sg_get_state(sg_solver* h, double* u, double* s) {
   if (s) {
     int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, false, h->stream, h->n_owned);
     if (rc) return rc;
-    SG_CUDA(cudaMemcpyAsync(s, h->sh.p, (size_t)h->n_owned * h->KS * 8, cudaMemcpyDeviceToHost, h->stream));
+    SG_CUDA(cudaMemcpyAsync(s, h->sh.p, (size_t)h->n_owned * h->KS_full * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   SG_CUDA(cudaStreamSynchronize(h->stream));
   return SG_OK;
@@ -733,7 +811,7 @@ int sg_get_field(sg_solver* h, int which, double* out) {
   if (!f) return fail(SG_EINVAL, "sg_get_field: bad field id");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->comm));
-  const int nc = field_ncomp(h, which);
+  const int nc = field_ncomp_boundary(h, which);
   DevBuf<double> tmp;   // test/diagnostic path: a private staging buffer keeps all four fields intact
   SG_CUDA(tmp.alloc((size_t)h->n_total * h->nd * nc));
   int rc = relayout(h, f->p, tmp.p, nc, false, h->stream, h->n_total);

@@ -78,6 +78,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// L2 prefetch of a contiguous block (no shared memory, no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   const uint32_t addr = smem_u32(bar);
@@ -109,9 +113,20 @@ struct StagePlan {
 __host__ __device__ constexpr uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
 __host__ __device__ constexpr uint32_t up128(uint32_t x) { return (x + 127u) & ~127u; }
 
-template <int D, int ND, int TILE, int NS, bool GTYPE, bool AXS, bool XS = GTYPE>
+// Stored stress components.  SYM = false: all D*D of them, as the reference's TensorFunctionSpace does
+// (elastic.py:81).  SYM = true: the upper triangle only -- Ds(u) is symmetric by construction (elastic.py:211-219),
+// so when s0 and the source are symmetric every stress field of the step is, bit for bit, and (i,j) / (j,i) need
+// not both travel through HBM (the library checks the premise, sg_set_state / sg_set_source -> SG_EASYM).
+template <int D, bool SYM> __host__ __device__ constexpr int ncs() { return SYM ? D * (D + 1) / 2 : D * D; }
+template <int D, bool SYM> __host__ __device__ constexpr int scomp(int i, int j) {
+  if (!SYM) return i * D + j;
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  return a * D - a * (a - 1) / 2 + (b - a);   // row-major upper triangle
+}
+
+template <int D, int ND, int TILE, int NS, bool GTYPE, bool AXS, bool XS = GTYPE, bool SYM = false>
 __host__ __device__ inline StagePlan make_plan(bool classes, bool per_cell_mat, bool sponge, int ftab_size) {
-  constexpr uint32_t KS = D * D * ND, KU = D * ND, NF = D + 1;
+  constexpr uint32_t KS = ncs<D, SYM>() * ND, KX = D * D * ND, KU = D * ND, NF = D + 1;
   constexpr uint32_t KIN = GTYPE ? KU : KS, KAX = GTYPE ? KS : KU;
   StagePlan p{};
   uint32_t o = 0;
@@ -136,7 +151,7 @@ __host__ __device__ inline StagePlan make_plan(bool classes, bool per_cell_mat, 
   p.ftab = o; o += up16((uint32_t)ftab_size);
   p.gtab = o; o += classes ? (uint32_t)(GEO_SMEM_CLASSES * D * D * 8) : 0;
   o = up128(o);
-  p.x = o; o += (GTYPE && XS) ? KS * TILE * 8 : 0;
+  p.x = o; o += (GTYPE && XS) ? KX * TILE * 8 : 0;
   p.total = o;
   return p;
 }
@@ -151,14 +166,14 @@ template <int D, int ND, int NFP, int TILE> struct FaceGeom {
 };
 
 // F-type: row i of  Dv(s)_i = sum_j d~_j s_ij   (free-surface trace on exterior facets: s^ = 0)
-template <int D, int ND, int NFP, int TILE> struct FCtx {
-  const double* own;          // &sIn[(i*D*ND)*TILE + lane]
+template <int D, int ND, int NFP, int TILE, int KS> struct FCtx {
+  const double* own;          // &sIn[lane]
   const double* tileS;        // sIn (shared)
   const double* gIn;          // global input field
   const unsigned char* sft;   // neighbour node table (shared)
   const FaceGeom<D, ND, NFP, TILE>* g;
   int tile;
-  int rowoff;                 // i*D*ND*TILE
+  int coff[D];                // coff[j] = row of s_ij (node 0) * TILE, for this thread's i
   // per-facet state
   const double* nbp;
   const unsigned char* row;
@@ -167,7 +182,7 @@ template <int D, int ND, int NFP, int TILE> struct FCtx {
   __device__ __forceinline__ void t(int b, double* t) const {
     double s[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) s[j] = own[(j * ND + b) * TILE];
+    for (int j = 0; j < D; ++j) s[j] = own[coff[j] + b * TILE];
 #pragma unroll
     for (int r = 0; r < D; ++r) {
       double a = g->ji[r][0] * s[0];
@@ -184,8 +199,7 @@ template <int D, int ND, int NFP, int TILE> struct FCtx {
     co = bnd ? 1.0 : 0.5;
     row = sft + (c & 0x7fu) * NFP;
     const int nt = n / TILE, nl = n % TILE;
-    const double* base = (nt == tile) ? (tileS + nl) : (gIn + (size_t)nt * (D * D * ND * TILE) + nl);
-    nbp = base + rowoff;
+    nbp = (nt == tile) ? (tileS + nl) : (gIn + (size_t)nt * (KS * TILE) + nl);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       if (f == 0) {
@@ -203,8 +217,8 @@ template <int D, int ND, int NFP, int TILE> struct FCtx {
     double acc = 0.0;
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      const double o = own[(j * ND + on) * TILE];
-      const double v = nbp[(j * ND + nn) * TILE];
+      const double o = own[coff[j] + on * TILE];
+      const double v = nbp[coff[j] + nn * TILE];
       acc = fma(gf[j], cn * v - co * o, acc);
     }
     return acc;
@@ -243,10 +257,10 @@ template <int D, int ND, int NFP, int TILE> struct GCtx {
 // ---------------------------------------------------------------------------------------------
 // producer side: one thread starts every bulk copy of a tile; they all complete on the stage's mbarrier
 // ---------------------------------------------------------------------------------------------
-template <int D, int ND, int TILE, bool GTYPE>
+template <int D, int ND, int TILE, bool GTYPE, bool SYM>
 __device__ __forceinline__ void issue_tile(const StageParams& p, const StagePlan& pl, unsigned char* stage,
                                            uint64_t* bar, int tile) {
-  constexpr int KS = D * D * ND, KU = D * ND, NF = D + 1;
+  constexpr int KS = ncs<D, SYM>() * ND, KU = D * ND, NF = D + 1;
   constexpr int KIN = GTYPE ? KU : KS, KAX = GTYPE ? KS : KU;
   const uint32_t total = pl.in_b + 2 * pl.ax_b + pl.nbr_b + pl.code_b + pl.geo_b + pl.mat_b + pl.abs_b;
   mbar_expect_tx(bar, total);
@@ -254,6 +268,11 @@ __device__ __forceinline__ void issue_tile(const StageParams& p, const StagePlan
   if (pl.ax_b) {
     bulk_g2s(stage + pl.ax0, p.ax0 + (size_t)tile * (KAX * TILE), pl.ax_b, bar);
     bulk_g2s(stage + pl.ax1, p.ax1 + (size_t)tile * (KAX * TILE), pl.ax_b, bar);
+  } else if (p.ax0 != nullptr) {
+    // AXPY operands read straight from global by the compute threads (large elements: no shared memory left to
+    // stage them): start them towards L2 now, a pipeline stage ahead of their use
+    bulk_prefetch_l2(p.ax0 + (size_t)tile * (KAX * TILE), KAX * TILE * 8);
+    bulk_prefetch_l2(p.ax1 + (size_t)tile * (KAX * TILE), KAX * TILE * 8);
   }
   bulk_g2s(stage + pl.nbr, p.nbr + (size_t)tile * (NF * TILE), pl.nbr_b, bar);
   bulk_g2s(stage + pl.code, p.code + (size_t)tile * pl.code_b, pl.code_b, bar);
@@ -332,7 +351,7 @@ __device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan&
     int t = blockIdx.x;                                                                                    \
     _Pragma("unroll") for (int s = 0; s < NS - 1; ++s) {                                                   \
       slot_tile[s] = t;                                                                                    \
-      if (t < p.ntiles) issue_tile<D, ND, TILE, GT>(p, pl, smem + s * pl.stage_bytes, bars + s, p.tile0 + t); \
+      if (t < p.ntiles) issue_tile<D, ND, TILE, GT, SYM>(p, pl, smem + s * pl.stage_bytes, bars + s, p.tile0 + t); \
       t = sched_next(p.sched);                                                                             \
     }                                                                                                      \
     t_ahead = t;                                                                                           \
@@ -344,7 +363,7 @@ __device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan&
     const int sn = (it + NS - 1) % NS;                                                                     \
     slot_tile[sn] = t_ahead;                                                                               \
     if (t_ahead < p.ntiles) {                                                                              \
-      issue_tile<D, ND, TILE, GT>(p, pl, smem + sn * pl.stage_bytes, bars + sn, p.tile0 + t_ahead);        \
+      issue_tile<D, ND, TILE, GT, SYM>(p, pl, smem + sn * pl.stage_bytes, bars + sn, p.tile0 + t_ahead);        \
       t_ahead = sched_next(p.sched);                                                                       \
     }                                                                                                      \
   }                                                                                                        \
@@ -356,14 +375,14 @@ __device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan&
 // Persistent CTAs with a dynamic tile scheduler; the bulk copies of the next NS-1 tiles are in flight while a
 // tile is computed.
 // ---------------------------------------------------------------------------------------------
-template <int D, int P, int TILE, int SPLIT, int MINB, int NS, bool AXPY, bool AXS>
+template <int D, int P, int TILE, int SPLIT, int MINB, int NS, bool AXPY, bool AXS, bool SYM>
 __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageParams p) {
   using E = ElemOps<D, P>;
-  constexpr int ND = E::ND, NFP = E::NFP, KU = D * ND, IPT = D / SPLIT, NT = TILE * SPLIT;
+  constexpr int ND = E::ND, NFP = E::NFP, KU = D * ND, KS = ncs<D, SYM>() * ND, IPT = D / SPLIT, NT = TILE * SPLIT;
   static_assert(D % SPLIT == 0, "SPLIT must divide D");
   extern __shared__ __align__(128) unsigned char smem[];
-  const StagePlan pl = make_plan<D, ND, TILE, NS, false, (AXPY && AXS)>(p.geoidx != nullptr, false,
-                                                                        p.absidx != nullptr, E::FTAB_SIZE);
+  const StagePlan pl = make_plan<D, ND, TILE, NS, false, (AXPY && AXS), false, SYM>(
+      p.geoidx != nullptr, false, p.absidx != nullptr, E::FTAB_SIZE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
   const unsigned char* sft = smem + pl.ftab;
   const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
@@ -386,17 +405,18 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     int aidx = -1;
     if (pl.abs_b) aidx = reinterpret_cast<const int32_t*>(stage + pl.abs)[lane];
 
-    FCtx<D, ND, NFP, TILE> c;
+    FCtx<D, ND, NFP, TILE, KS> c;
     c.tileS = sIn;
     c.gIn = p.in;
     c.sft = sft;
     c.g = &g;
     c.tile = tile;
+    c.own = sIn + lane;
 #pragma unroll
     for (int ii = 0; ii < IPT; ++ii) {
       const int i = ig * IPT + ii;
-      c.rowoff = i * D * ND * TILE;
-      c.own = sIn + c.rowoff + lane;
+#pragma unroll
+      for (int j = 0; j < D; ++j) c.coff[j] = scomp<D, SYM>(i, j) * (ND * TILE);
       double acc[ND];
 #pragma unroll
       for (int a = 0; a < ND; ++a) acc[a] = 0.0;
@@ -439,14 +459,14 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
 //                out_ij = c0*ax0_ij + c1*ax1_ij + c2*(...)                                   (K6, AXPY)
 // XREG (only with SPLIT == 1): the gradients G_ij stay in registers instead of the shared X buffer.
 // ---------------------------------------------------------------------------------------------
-template <int D, int P, int TILE, int SPLIT, int MINB, int NS, bool AXPY, bool AXS, bool XREG>
+template <int D, int P, int TILE, int SPLIT, int MINB, int NS, bool AXPY, bool AXS, bool XREG, bool SYM>
 __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageParams p) {
   using E = ElemOps<D, P>;
-  constexpr int ND = E::ND, NFP = E::NFP, KS = D * D * ND, IPT = D / SPLIT, NT = TILE * SPLIT;
+  constexpr int ND = E::ND, NFP = E::NFP, KS = ncs<D, SYM>() * ND, KX = D * D * ND, IPT = D / SPLIT, NT = TILE * SPLIT;
   static_assert(!XREG || SPLIT == 1, "register-resident gradients need one thread per cell");
   extern __shared__ __align__(128) unsigned char smem[];
-  const StagePlan pl = make_plan<D, ND, TILE, NS, true, (AXPY && AXS), !XREG>(p.geoidx != nullptr, p.mat != nullptr,
-                                                                              false, E::FTAB_SIZE);
+  const StagePlan pl = make_plan<D, ND, TILE, NS, true, (AXPY && AXS), !XREG, SYM>(
+      p.geoidx != nullptr, p.mat != nullptr, false, E::FTAB_SIZE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
   const unsigned char* sft = smem + pl.ftab;
   const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
     c.sft = sft;
     c.g = &g;
     c.tile = tile;
-    double XR[XREG ? KS : 1];
+    double XR[XREG ? KX : 1];
 #pragma unroll
     for (int ii = 0; ii < IPT; ++ii) {
       const int i = ig * IPT + ii;
@@ -525,11 +545,14 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
         for (int k = 1; k < D; ++k) div += XREG ? XR[(k * D + k) * ND + a] : X[((k * D + k) * ND + a) * TILE];
         const double ld = lam * div;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
+        for (int jj = 0; jj < D; ++jj) {
+          // SYM: row i produces (i,i) and (i,i+1 mod D) [D = 3] / row 0 produces (0,0), (0,1), row 1 (1,1) [D = 2]
+          const int j = SYM ? (i + jj) % D : jj;
+          if (SYM && !(D == 2 ? (jj == 0 || i == 0) : (jj < 2))) continue;
           double v = XREG ? mu * (XR[(i * D + j) * ND + a] + XR[(j * D + i) * ND + a])
                           : mu * (X[((i * D + j) * ND + a) * TILE] + X[((j * D + i) * ND + a) * TILE]);
           if (j == i) v += ld;
-          const int o = ((i * D + j) * ND + a) * TILE + lane;
+          const int o = (scomp<D, SYM>(i, j) * ND + a) * TILE + lane;
           if (AXPY && AXS) {
             const double* a0 = reinterpret_cast<const double*>(stage + pl.ax0);
             const double* a1 = reinterpret_cast<const double*>(stage + pl.ax1);
@@ -555,24 +578,44 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
 // ---------------------------------------------------------------------------------------------
 // small utility kernels
 // ---------------------------------------------------------------------------------------------
-// boundary (AoS, cell-major: [cell][node][comp]) <-> device (tile-blocked SoA: [tile][comp*ND+node][lane])
+// boundary (AoS, cell-major: [cell][node][comp]) <-> device (tile-blocked SoA: [tile][comp*ND+node][lane]).
+// symd = 0: the device stores the ncomp boundary components as they are.  symd = D > 0 (stress fields of a
+// symmetric-storage solver): the boundary has D*D components, the device the upper triangle; on the way in the
+// two halves are compared and *asym is raised if they differ, on the way out (j,i) is filled from (i,j).
 template <bool TO_DEVICE>
 __global__ void relayout_kernel(double* __restrict__ dev, double* __restrict__ host_order, int64_t ncell,
-                                int64_t n_owned, int64_t n_owned_pad, int nd, int ncomp, int tile) {
-  const int K = nd * ncomp;
-  const int64_t total = ncell * K;
+                                int64_t n_owned, int64_t n_owned_pad, int nd, int ncomp, int tile, int symd,
+                                unsigned int* __restrict__ asym) {
+  const int KH = nd * ncomp;                                        // boundary doubles per cell
+  const int K = symd ? nd * (symd * (symd + 1) / 2) : KH;           // device rows per cell
+  const int64_t total = ncell * KH;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t cell = idx / K;
-    const int r = (int)(idx % K);
+    const int64_t cell = idx / KH;
+    const int r = (int)(idx % KH);
     const int node = r / ncomp, comp = r % ncomp;
-    const int64_t k = comp * nd + node;
+    int dcomp = comp;
+    bool lower = false;
+    if (symd) {
+      const int i = comp / symd, j = comp % symd;
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      dcomp = a * symd - a * (a - 1) / 2 + (b - a);
+      lower = i > j;
+    }
+    const int64_t k = dcomp * nd + node;
     const int64_t e = cell < n_owned ? cell : cell - n_owned + n_owned_pad;
     const int64_t d = ((e / tile) * K + k) * tile + e % tile;
-    if (TO_DEVICE)
-      dev[d] = host_order[idx];
-    else
+    if (TO_DEVICE) {
+      const double v = host_order[idx];
+      if (!lower) {
+        dev[d] = v;
+      } else {
+        const double w = host_order[idx - comp + (comp % symd) * symd + comp / symd];   // the (j,i) entry
+        if (v != w && !(v != v && w != w)) *asym = 1u;
+      }
+    } else {
       host_order[idx] = dev[d];
+    }
   }
 }
 

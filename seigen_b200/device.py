@@ -21,7 +21,7 @@ __all__ = ["DeviceSolver"]
 
 class DeviceSolver:
     def __init__(self, mesh: Mesh, degree: int, device: int = 0, plan: RankPlan | None = None,
-                 geom_classes: bool = True):
+                 geom_classes: bool = True, symmetric: bool = False):
         self.mesh = mesh
         self.dim = mesh.dim
         self.degree = int(degree)
@@ -37,7 +37,8 @@ class DeviceSolver:
         desc = capi.MeshDesc(dim=self.dim, degree=self.degree, n_owned=plan.n_owned, n_total=plan.n_total,
                              nbr=nbr.ctypes.data, code=code.ctypes.data, jinv=jinv.ctypes.data,
                              device=int(device), n_boundary=int(plan.n_boundary),
-                             geom_classes=int(bool(geom_classes)), reserved=0)
+                             geom_classes=int(bool(geom_classes)), symmetric_stress=int(bool(symmetric)))
+        self.symmetric = bool(symmetric)
         check(lib.sg_create(C.byref(self._h), C.byref(desc)))
         self.n_owned = plan.n_owned
         self.n_total = plan.n_total

@@ -141,6 +141,12 @@ class ExplicitElasticLF4(ElasticLF4):
         self.halo_mode = None
         self.steps_done = 0
         self.last_run_ms = None
+        #: keep only the upper triangle of the stress fields on the device (include/seigen_b200.h,
+        #: sg_mesh_desc.symmetric_stress).  Tried first; if s0 or the source turns out not to be symmetric the
+        #: solver is rebuilt with full storage (all ranks together) and stays that way.  SG_SYM=0 disables it.
+        import os
+        self._symmetric = os.environ.get("SG_SYM", "1") != "0"
+        self._last_times = []
 
     # -- device setup -----------------------------------------------------------------------------------------
     def _ensure_device(self):
@@ -150,7 +156,7 @@ class ExplicitElasticLF4(ElasticLF4):
                 raise capi.SgError("no CUDA device: seigen_b200 has no CPU fallback")
             plan = mesh_plan(self.mesh)
             device = torch.cuda.current_device()
-            self._dev = DeviceSolver(self.mesh, self.S.degree, device=device, plan=plan)
+            self._dev = DeviceSolver(self.mesh, self.S.degree, device=device, plan=plan, symmetric=self._symmetric)
             if plan.nranks > 1:
                 import os
                 self.halo_mode = os.environ.get("SG_HALO", "peer")
@@ -163,15 +169,49 @@ class ExplicitElasticLF4(ElasticLF4):
                     # library transport: pack -> NCCL send/recv -> unpack, driven pass by pass from the host
                     from .halo import HaloExchanger
                     nd, d = self.S.elem.nd, self.dimension
-                    self._halo = HaloExchanger(plan, nd * d * d, torch.device("cuda", device))
+                    self._halo = HaloExchanger(plan, nd * d * d, torch.device("cuda", device))   # sized for full storage
                     self._comm_stream = torch.cuda.ExternalStream(lib.sg_stream(self._dev.handle, 1), device=device)
                 else:
                     raise ValueError("SG_HALO must be 'peer' or 'nccl'")
         return self._dev
 
+    def _agree_asymmetric(self, flag):
+        """True on every rank if any rank found its share of s0 / of the source asymmetric."""
+        plan = mesh_plan(self.mesh)
+        if plan.nranks == 1:
+            return bool(flag)
+        import torch
+        import torch.distributed as dist
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.tensor([1.0 if flag else 0.0], device="cuda" if on_gpu else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
+    def _fall_back_to_full_storage(self):
+        log("stress or source not symmetric: switching to full stress storage")
+        self._symmetric = False
+        if self._dev is not None:
+            self._dev.close()
+        self._dev = None
+        self._halo = None
+        self._source_key = None
+
     def setup(self, times=None):
         """Upload parameters (the role of elastic.py:244-255 + 369-385: nothing is assembled or inverted here,
         the inverse mass is folded into the reference-element matrices)."""
+        self._last_times = list(times or [])
+        if not self._symmetric:
+            return self._setup_once(times)
+        asym = False
+        try:
+            self._setup_once(times)
+        except capi.SgAsymmetric:
+            asym = True
+        if self._agree_asymmetric(asym):
+            self._fall_back_to_full_storage()
+            self._setup_once(times)
+
+    def _setup_once(self, times=None):
         log("Creating solver contexts")
         with timed_region('solver setup'):
             for name in ("density", "dt", "mu", "l"):
@@ -299,7 +339,18 @@ class ExplicitElasticLF4(ElasticLF4):
         # u0 / s0 may be pending copies of u1 / s1 from the previous run(): upload from where the bytes are
         u = self.u0.dat.current_source().data
         s = self.s0.dat.current_source().data
-        check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+        if self._symmetric:
+            asym = False
+            try:
+                check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+            except capi.SgAsymmetric:
+                asym = True
+            if self._agree_asymmetric(asym):
+                self._fall_back_to_full_storage()
+                self._setup_once(self._last_times)
+                check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+        else:
+            check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
         if self._dev.plan.nranks > 1 and self._halo is None:
             check(lib.sg_exchange(self._dev.handle, capi.FIELD_U))
             check(lib.sg_exchange(self._dev.handle, capi.FIELD_S))
@@ -319,7 +370,8 @@ class ExplicitElasticLF4(ElasticLF4):
         import torch
         dev, halo = self._dev, self._halo
         nd, d = self.S.elem.nd, self.dimension
-        K = nd * (d if which in (capi.FIELD_U, capi.FIELD_UH) else d * d)
+        ncs = d * (d + 1) // 2 if dev.symmetric else d * d            # stress components stored on the device
+        K = nd * (d if which in (capi.FIELD_U, capi.FIELD_UH) else ncs)
         check(lib.sg_comm_wait_compute(dev.handle))
         check(lib.sg_pack(dev.handle, which, halo.sendbuf.data_ptr(), 1))
         with torch.cuda.stream(self._comm_stream):
@@ -353,10 +405,10 @@ class ExplicitElasticLF4(ElasticLF4):
         self.write(self.u1, self.s1)                      # initial condition, as elastic.py:273
         times = step_times(T, self.dt) if self.dt else []
         self.setup(times)
-        dev = self._dev
         with timed_region('timestepping'):
             with timed_region('state upload'):
                 self._upload_state()
+            dev = self._dev                               # (the upload may have rebuilt it with full stress storage)
             if self.output:
                 for n in range(len(times)):
                     self._advance(1, n)

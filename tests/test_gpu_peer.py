@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, dim, p, nsteps, out_dir, mode):
+def _worker(rank, world, port, dim, p, nsteps, out_dir, mode, symmetric):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,6 +37,8 @@ def _worker(rank, world, port, dim, p, nsteps, out_dir, mode):
         E, nd = mesh.num_cells(), el.S.elem.nd
         u0 = rng.standard_normal((E, nd, dim))
         s0 = rng.standard_normal((E, nd, dim, dim))
+        if symmetric:
+            s0 = 0.5 * (s0 + np.swapaxes(s0, 2, 3))
         el.u0.dat.data[...] = u0[g].reshape(el.u0.dat.data.shape)
         el.s0.dat.data[...] = s0[g].reshape(el.s0.dat.data.shape)
         u1, s1 = el.run((nsteps + 0.5) * el.dt)
@@ -47,18 +49,22 @@ def _worker(rank, world, port, dim, p, nsteps, out_dir, mode):
         err = ctypes.c_int64()
         check(lib.sg_peer_error(el._dev.handle, ctypes.byref(err)))
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), g=g, u=u1.dat.data, s=s1.dat.data, err=err.value,
-                 steps=el.steps_done, mode=el.halo_mode)
+                 steps=el.steps_done, mode=el.halo_mode, packed=el._dev.symmetric)
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dim,p,world", [(2, 2, 2), (2, 1, 3), (3, 1, 2)])
-def test_peer_exchange_matches_oracle(tmp_path, dim, p, world):
+@pytest.mark.parametrize("dim,p,world,symmetric", [(2, 2, 2, False), (2, 1, 3, False), (3, 1, 2, False),
+                                                   (2, 2, 2, True), (3, 1, 2, True)])
+def test_peer_exchange_matches_oracle(tmp_path, dim, p, world, symmetric):
+    """symmetric = False: random s0, so every rank starts with packed stress storage, finds its share asymmetric
+    and all ranks fall back to full storage together; True: the packed layout travels through the halo exchange."""
     import torch.multiprocessing as mp
     from oracle.elastic_oracle import ElasticOracle
     nsteps = 3
-    mp.spawn(_worker, args=(world, _free_port(), dim, p, nsteps, str(tmp_path), "peer"), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), dim, p, nsteps, str(tmp_path), "peer", symmetric), nprocs=world,
+             join=True)
     mesh = small_mesh(dim, n=12 if dim == 2 else 4)
     orc = ElasticOracle(mesh.coords, mesh.cells, p)
     orc.l, orc.mu, orc.density, orc.dt = 0.5, 0.25, 1.0, 2e-3
@@ -66,12 +72,15 @@ def test_peer_exchange_matches_oracle(tmp_path, dim, p, world):
     E, nd = mesh.num_cells(), orc.nd
     u = rng.standard_normal((E, nd, dim))
     s = rng.standard_normal((E, nd, dim, dim))
+    if symmetric:
+        s = 0.5 * (s + np.swapaxes(s, 2, 3))
     for _ in range(2 * nsteps):
         u, s, _ = orc.step(u, s, 0.0)
     seen = np.zeros(E, dtype=int)
     for r in range(world):
         z = np.load(tmp_path / f"r{r}.npz")
         assert int(z["err"]) == 0 and int(z["steps"]) == nsteps and str(z["mode"]) == "peer"
+        assert bool(z["packed"]) == symmetric
         g = z["g"]
         seen[g] += 1
         assert rel_err(z["u"].reshape(len(g), nd, dim), u[g]) < 1e-10
