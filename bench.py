@@ -118,14 +118,15 @@ RICKER = ("x[0] >= {x0} && x[0] <= {x1} && x[1] >= {y0} && x[1] <= {y1} ? "
           "(-1.0 + 2*a*pow(t - t0, 2))*exp(-a*pow(t - t0, 2)) : 0.0")
 
 
-def marmousi_problem(nranks, scale=1.0):
+def marmousi_problem(nranks, scale=1.0, strong=False):
     """ElasticLF4 set up through the public API exactly as a reference script would (tests/explosive_source/
     explosive_source_lf4.py:9-52), on this rank's share of the weak-scaled Marmousi mesh."""
     from seigen_b200 import ElasticLF4, Expression, Function, RectangleMesh
     from seigen_b200.marmousi import marmousi_lame_at
 
     nx, ny = max(2, int(round(NX * scale))), max(2, int(round(NY * scale)))
-    mesh = RectangleMesh(nx * nranks, ny, LX * nranks, LY)
+    ntile = 1 if strong else nranks          # strong scaling: the one 53 M-DoF model is cut into nranks parts
+    mesh = RectangleMesh(nx * ntile, ny, LX * ntile, LY)
     el = ElasticLF4.create(mesh, "DG", DEGREE, dimension=2, solver="explicit", output=False)
     order = el.S.cell_order
     cent = mesh.coords[mesh.cells[order]].mean(axis=1)
@@ -137,7 +138,7 @@ def marmousi_problem(nranks, scale=1.0):
     fpeak = 10.0
     a = (np.pi * fpeak) ** 2
     boxes = []
-    for r in range(nranks):
+    for r in range(ntile):
         xc = LX * (r + 0.5)
         boxes.append(RICKER.format(x0=xc - 0.5 * h, x1=xc + 0.5 * h, y0=LY - 1.5 * h, y1=LY - 0.5 * h))
     src = " + ".join("(" + b + ")" for b in boxes)
@@ -148,7 +149,7 @@ def marmousi_problem(nranks, scale=1.0):
     el.u0.dat.data[...] = 1e-3 * rng.standard_normal(el.u0.dat.data.shape)
     s0 = 1e-3 * rng.standard_normal(el.s0.dat.data.shape)
     el.s0.dat.data[...] = 0.5 * (s0 + np.swapaxes(s0, 1, 2))      # a stress tensor: symmetric
-    name = f"marmousi_2d_p{DEGREE}_{nx}x{ny}_per_gpu"
+    name = f"marmousi_2d_p{DEGREE}_{nx}x{ny}_" + ("total" if strong else "per_gpu")
     return el, name
 
 
@@ -253,7 +254,8 @@ def run_gpu(args):
         return float(t.item())
 
     t_setup = time.perf_counter()
-    el, wname = marmousi_problem(world, args.scale)
+    strong = args.scaling == "strong"
+    el, wname = marmousi_problem(world, args.scale, strong)
     K, W = args.steps, max(3, args.warmup)
     dt = float(el.dt)
     T = (K + 0.5) * dt
@@ -287,7 +289,13 @@ def run_gpu(args):
     reps = max(10, min(K, 50))
     stage_ms = [dev.time_stage(k, dt * 1e-3, reps) for k in range(1, 7)]
     E = dev.n_owned
-    cell_doubles = {1: 6, 2: 6, 3: 10, 4: 6, 5: 6, 6: 14}       # field doubles per node per pass
+    # field doubles per node per pass: algorithmic = the reference's full d*d stress storage (SURVEY.md 8d,
+    # DESIGN.md section 4); moved = what this solver really reads + writes (upper triangle when the stress is symmetric)
+    ncs = d * (d + 1) // 2 if dev.symmetric else d * d
+
+    def pass_doubles(S, U):
+        return {1: S + U, 2: S + U, 3: S + 3 * U, 4: S + U, 5: S + U, 6: U + 3 * S}
+    cell_doubles, moved_doubles = pass_doubles(d * d, d), pass_doubles(ncs, d)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -298,15 +306,26 @@ def run_gpu(args):
     stages = []
     for k in range(1, 7):
         b = cell_doubles[k] * nd * 8.0 * E
-        stages.append({"pass": f"K{k}", "ms": stage_ms[k - 1], "alg_bytes": b, "gbs": b / stage_ms[k - 1] / 1e6})
+        mb = moved_doubles[k] * nd * 8.0 * E
+        stages.append({"pass": f"K{k}", "ms": stage_ms[k - 1], "alg_bytes": b, "gbs": b / stage_ms[k - 1] / 1e6,
+                       "moved_bytes": mb, "moved_gbs": mb / stage_ms[k - 1] / 1e6})
     dom = stages[5]
     roofline = {"kernel": "stage_g_kernel<2,2,AXPY> (pass K6: s1 = s0 + dt*sh1 + dt^3/24*(Ds(utemp)+src))",
                 "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
                 "traffic": profiled_traffic(), "peak_source": peak_src,
-                "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"]}
+                "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"],
+                "moved_bytes_per_launch": dom["moved_bytes"], "moved_gbs": dom["moved_gbs"],
+                "moved_frac": dom["moved_gbs"] / peak,
+                "note": "achieved/frac use the ALGORITHMIC bytes of SURVEY.md 8d (full d*d stress: 14*nd*8 B per cell "
+                        "for K6); with symmetric stress storage the kernel moves only moved_bytes_per_launch "
+                        "(11*nd*8 B per cell), so frac can exceed moved_frac -- moved_frac is the kernel's real "
+                        "HBM efficiency, frac the speed-up-relevant one"}
     step_gbs = 64.0 * ndof_local * K / (ms_local * 1e-3) / 1e9
+    moved_per_dof = 8.0 * sum(moved_doubles.values()) / (d + d * d)
     roofline_step = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
-                     "alg_bytes_per_dof_step": 64, "note": "per GPU, whole step = 6 passes"}
+                     "alg_bytes_per_dof_step": 64, "moved_bytes_per_dof_step": moved_per_dof,
+                     "moved_frac": step_gbs * moved_per_dof / 64.0 / peak,
+                     "note": "per GPU, whole step = 6 passes"}
 
     # ---- e2e: ElasticLF4.run(T), host page-locked state in and out inside the timed region -------------------
     el.run(T)                                   # warm: source table for these K steps, graph
@@ -343,7 +362,7 @@ def run_gpu(args):
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
                "config": {"workload": wname, "degree": DEGREE, "dim": 2, "cells_per_gpu": int(E),
                           "dof_per_gpu": int(ndof_local), "dof_total": int(ndof), "dt": dt,
@@ -351,7 +370,10 @@ def run_gpu(args):
                           "source": "Ricker, one cell box per tile", "sponge": "none",
                           "initial_data": "random 1e-3 velocity, random 1e-3 symmetric stress",
                           "stress_storage": "symmetric (upper triangle)" if dev.symmetric else "full",
-                          "l2": "state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)" % (8e-6 * ndof_local),
+                          "l2": ("state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)"
+                                 if 8 * ndof_local > 126e6 else
+                                 "state 8*dof_per_gpu bytes = %.0f MB fits the 126 MB L2: not an HBM measurement "
+                                 "(strong-scaling / reduced-scale run)") % (8e-6 * ndof_local),
                           "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass, exchange={el.halo_mode}",
                           "setup_s": t_setup},
                "roofline": roofline, "roofline_step": roofline_step, "stages": stages,
@@ -370,6 +392,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="mesh resolution factor (development aid; 1 = headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's scaling run): 53.4 M DoF per GPU; strong: 53.4 M DoF in total")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

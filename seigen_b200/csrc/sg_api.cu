@@ -93,19 +93,13 @@ const std::vector<Variant>& variants() {
       make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>(),
       make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>(),
       make_variant<3, 1, 64, 1, 4, 3, 2, 2, true, false>(),
-      make_variant<3, 1, 64, 1, 8, 4, 2, 2, true, false>(),
       make_variant<3, 1, 64, 1, 6, 3, 2, 2, true, false>(),
-      make_variant<3, 1, 128, 1, 4, 2, 2, 2, true, false>(),
       make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>(),
       make_variant<3, 1, 32, 3, 4, 4, 3, 2, true, false>(),
-      make_variant<3, 1, 64, 3, 4, 3, 2, 2, true, false>(),
       make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>(),
       make_variant<3, 2, 32, 3, 4, 4, 2, 2, true, false>(),
-      make_variant<3, 2, 32, 3, 5, 4, 2, 2, true, false>(),
-      make_variant<3, 2, 64, 3, 2, 2, 2, 1, true, false>(),
+      make_variant<3, 3, 32, 3, 2, 2, 2, 2, false, false>(),
       make_variant<3, 3, 32, 3, 2, 2, 2, 1, false, false>(),
-      make_variant<3, 3, 32, 3, 3, 3, 2, 1, false, false>(),
-      make_variant<3, 3, 32, 3, 4, 3, 1, 1, false, false>(),
   };
   return v;
 }

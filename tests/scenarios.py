@@ -90,3 +90,22 @@ def explosive_oracle(Lx, Ly, h, courant=0.05, degree=2, sigma_degree=4):
         out[active] = source.evaluate(xs[active], t=t)
         return out.reshape(orc.E, orc.nd, 2, 2)
     return mesh, orc, src
+
+
+# ---- 3D Gaussian pulse on a tetrahedral box (BASELINE.json configs[2]) --------------------
+# 3-D lift of tests/pulse/pulse_1d_lf4.py: rho = 1, mu = 0.25, lambda = 0.5 (:14-17), u = (G, 0, 0), s = -G I with
+# G = exp(-50 (x-1)^2) (:27-30), DG1 sponge sigma = 100 near both ends in x (:22-24).
+PULSE_MU, PULSE_LAM = 0.25, 0.5
+
+
+def pulse_expressions():
+    g = "exp(-50*pow(x[0] - 1.0, 2))"
+    u0 = Expression((g, "0.0", "0.0"))
+    s0 = Expression((("-" + g, "0.0", "0.0"), ("0.0", "-" + g, "0.0"), ("0.0", "0.0", "-" + g)))
+    sponge = Expression("x[0] >= 3.5 || x[0] <= 0.5 ? 100.0 : 0")
+    return u0, s0, sponge
+
+
+def pulse_dt(h, p):
+    """min(0.5 h / (2^(p-1) Vp), 1/sigma_max) with Vp = 1, sigma_max = 100."""
+    return min(0.5 * h / (2 ** (p - 1) * 1.0), 1.0 / 100.0)

@@ -25,7 +25,8 @@ def _worker(rank, world, port, dim, p, nsteps, out_dir, mode, symmetric):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["SG_HALO"] = mode
-    torch.cuda.set_device(0)
+    # SG_TEST_SPREAD=1 (multi-GPU box): one rank per GPU, so the rows really cross NVLink; default: all on cuda:0
+    torch.cuda.set_device(rank % torch.cuda.device_count() if os.environ.get("SG_TEST_SPREAD") else 0)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from seigen_b200 import ElasticLF4

@@ -140,3 +140,42 @@ def test_run_twice_continues_and_output_mode(tmp_path, monkeypatch):
     assert rel_err(ub.dat.data, ua) < 1e-12
     assert np.array_equal(b.elastic.u0.dat.data, ub.dat.data)
     assert len(list(tmp_path.glob("velocity_*.vtk"))) == 2 * (n1 + 1)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_pulse_3d_parity(p):
+    """BASELINE.json configs[2]: 3D Gaussian pulse on a tetrahedral box, DG P1-P3, DG1 sponge, through the public API,
+    against the C restatement of the oracle on the same mesh (box [0,4]x[0,1]x[0,1] at a quarter of the headline
+    resolution so that the oracle finishes in seconds; the full-size case runs in test_gpu_properties.py)."""
+    from oracle.c_oracle import COracle
+    from oracle.elastic_oracle import ElasticOracle
+    from seigen_b200 import BoxMesh, ElasticLF4, Function, FunctionSpace
+    from tests.scenarios import PULSE_LAM, PULSE_MU, pulse_dt, pulse_expressions
+    nx = 16
+    mesh = BoxMesh(nx, nx // 4, nx // 4, 4.0, 1.0, 1.0)
+    u_e, s_e, sponge = pulse_expressions()
+    el = ElasticLF4.create(mesh, "DG", p, dimension=3, solver="explicit", output=False)
+    el.density, el.mu, el.l = 1.0, PULSE_MU, PULSE_LAM
+    el.dt = pulse_dt(4.0 / nx, p)
+    el.absorption_function = Function(FunctionSpace(mesh, "DG", 1))
+    el.absorption = sponge
+    el.u0.interpolate(u_e)
+    el.s0.interpolate(s_e)
+    nsteps = {1: 200, 2: 100, 3: 60}[p]
+    u0 = el.u0.dat.data.copy()
+    s0 = el.s0.dat.data.copy()
+    u1, s1 = el.run((nsteps + 0.5) * el.dt)
+    assert el.steps_done == nsteps and el._dev.symmetric           # a symmetric stress: packed storage is kept
+
+    order = el.S.cell_order
+    orc = ElasticOracle(mesh.coords, mesh.cells[order], p, sigma_degree=1)
+    orc.l, orc.mu, orc.density, orc.dt = PULSE_LAM, PULSE_MU, 1.0, el.dt
+    orc.sigma = el.absorption_function.dat.data.reshape(orc.E, -1)
+    co = COracle(orc)
+    u = u0.reshape(orc.E, orc.nd, 3).copy()
+    s = s0.reshape(orc.E, orc.nd, 3, 3).copy()
+    for _ in range(nsteps):
+        co.step_inplace(u, s, None, el.dt)
+    assert np.abs(u).max() < 10.0                                  # stable (SURVEY.md Appendix C)
+    assert rel_err(u1.dat.data.reshape(u.shape), u) < 1e-10
+    assert rel_err(s1.dat.data.reshape(s.shape), s) < 1e-10
