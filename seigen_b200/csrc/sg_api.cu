@@ -323,6 +323,7 @@ int field_ncomp_boundary(sg_solver* h, int which);
 int enqueue_exchange(sg_solver* h, int which, cudaStream_t st) {
   if (h->npeers == 0) return SG_OK;
   const int K = field_ncomp(h, which) * h->nd;
+  // (a single push+signal+wait kernel was tried and was slower: profiles/r01_experiment_fused_exchange.log)
   sg::push_kernel<<<grid_for(h->nsend * K), 256, 0, st>>>(field_buf(h, which)->p, h->send_cells.p, h->send_dst.p,
                                                           h->send_peer.p, h->rfield.p + (size_t)which * h->npeers,
                                                           h->nsend, K, h->tile);

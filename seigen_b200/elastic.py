@@ -223,9 +223,16 @@ class ExplicitElasticLF4(ElasticLF4):
             if np.ndim(lam) or np.ndim(mu):
                 lam = np.broadcast_to(np.asarray(lam, dtype=float), (n_owned,))
                 mu = np.broadcast_to(np.asarray(mu, dtype=float), (n_owned,))
-                lam_c, mu_c = np.ascontiguousarray(lam), np.ascontiguousarray(mu)
-                check(lib.sg_set_material(dev.handle, float(self.density), 0.0, 0.0, ptr(lam_c), ptr(mu_c)))
+                # per-cell tables are re-tiled and uploaded by the library: skip it when this solver already holds
+                # exactly these values (run() is called repeatedly in the reference's scripts and in bench.py)
+                last = getattr(self, "_material_on_device", None)
+                if not (last is not None and last[0] is dev and last[1] == float(self.density)
+                        and np.array_equal(last[2], lam) and np.array_equal(last[3], mu)):
+                    lam_c, mu_c = np.ascontiguousarray(lam), np.ascontiguousarray(mu)
+                    check(lib.sg_set_material(dev.handle, float(self.density), 0.0, 0.0, ptr(lam_c), ptr(mu_c)))
+                    self._material_on_device = (dev, float(self.density), lam_c.copy(), mu_c.copy())
             else:
+                self._material_on_device = None
                 check(lib.sg_set_material(dev.handle, float(self.density), float(lam), float(mu), None, None))
             self._upload_absorption()
             self._upload_source(times or [])
@@ -278,6 +285,7 @@ class ExplicitElasticLF4(ElasticLF4):
             nodes = np.flatnonzero(active)
             if len(nodes) == 0:
                 check(lib.sg_set_source(dev.handle, 0, None, 0, None))
+                self._source_key = key       # "no source on this rank" is a result too: do not probe again
                 return
             xs = x[nodes]
             amp = np.zeros((len(times), len(nodes) * d * d))
