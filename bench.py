@@ -221,6 +221,9 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
+    from seigen_b200 import helpers
+    helpers.LOG_STREAM = sys.stderr            # stdout carries the one JSON line and nothing else
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (seigen_b200 has no CPU fallback; use --impl reference for the CPU arm)")
     world = env_int("WORLD_SIZE", 1)

@@ -14,10 +14,14 @@ def _rank():
         return 0
 
 
+#: where ``log`` writes; bench.py points it at stderr so that its stdout is exactly one JSON line
+LOG_STREAM = None
+
+
 def log(s):
     """Rank-0 print (helpers.py:6-12)."""
     if _rank() == 0:
-        print(s)
+        print(s, file=LOG_STREAM)
 
 
 def Vp(mu, l, density):
