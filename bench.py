@@ -153,6 +153,27 @@ def marmousi_problem(nranks, scale=1.0, strong=False):
     return el, name
 
 
+BOX3D_N = {1: 26, 2: 33, 4: 41, 8: 52}     # 25.3 / 51.7 / 99.2 / 202.5 M DoF at P3
+
+
+def box3d_problem(nranks):
+    """BASELINE.json configs[4] (--workload box3d): UnitCubeMesh(N) of Kuhn tetrahedra, DG P3 (240 DoF per cell),
+    weak-scaled with N = 26 / 33 / 41 / 52 for 1 / 2 / 4 / 8 GPUs (~25 M DoF per GPU), rho = 1, mu = 0.25,
+    lambda = 0.5, dt = 0.5 h / (2^(p-1) Vp) as tests/eigenmode/eigenmode_3d.py:72-79, random 1e-3 initial data."""
+    from seigen_b200 import ElasticLF4, UnitCubeMesh
+    p = 3
+    N = BOX3D_N.get(nranks) or int(round(26 * nranks ** (1.0 / 3.0)))
+    mesh = UnitCubeMesh(N, N, N)
+    el = ElasticLF4.create(mesh, "DG", p, dimension=3, solver="explicit", output=False)
+    el.density, el.l, el.mu = 1.0, 0.5, 0.25
+    el.dt = 0.5 * (1.0 / N) / (2 ** (p - 1) * 1.0)
+    rng = np.random.default_rng(4321 + el.S.plan.rank)
+    el.u0.dat.data[...] = 1e-3 * rng.standard_normal(el.u0.dat.data.shape)
+    s0 = 1e-3 * rng.standard_normal(el.s0.dat.data.shape)
+    el.s0.dat.data[...] = 0.5 * (s0 + np.swapaxes(s0, 1, 2))
+    return el, f"box3d_p{p}_unitcube_{N}"
+
+
 def sample_problem():
     """Bounded CPU sample of the same workload: the Marmousi grid at its native h = 24 m (seigen/marmousi.py:18-21),
     P2 -- 92 686 cells, 3 336 696 DoF, same materials rule, same dt rule."""
@@ -258,14 +279,17 @@ def run_gpu(args):
 
     t_setup = time.perf_counter()
     strong = args.scaling == "strong"
-    el, wname = marmousi_problem(world, args.scale, strong)
+    if args.workload == "box3d":
+        el, wname = box3d_problem(world)
+    else:
+        el, wname = marmousi_problem(world, args.scale, strong)
     K, W = args.steps, max(3, args.warmup)
     dt = float(el.dt)
     T = (K + 0.5) * dt
     # first run(): builds the rank plan, uploads geometry/material/source table, captures the graph (untimed)
     el.run((W + 0.5) * dt)
     dev = el._dev
-    nd, d = el.S.elem.nd, 2
+    nd, d = el.S.elem.nd, el.dimension
     ndof_local = dev.n_owned * nd * (d + d * d)
     ndof = sum_over_ranks(ndof_local)
     t_setup = time.perf_counter() - t_setup
@@ -313,16 +337,17 @@ def run_gpu(args):
         stages.append({"pass": f"K{k}", "ms": stage_ms[k - 1], "alg_bytes": b, "gbs": b / stage_ms[k - 1] / 1e6,
                        "moved_bytes": mb, "moved_gbs": mb / stage_ms[k - 1] / 1e6})
     dom = stages[5]
-    roofline = {"kernel": "stage_g_kernel<2,2,AXPY> (pass K6: s1 = s0 + dt*sh1 + dt^3/24*(Ds(utemp)+src))",
+    roofline = {"kernel": "stage_g_kernel<%d,%d,AXPY> (pass K6: s1 = s0 + dt*sh1 + dt^3/24*(Ds(utemp)+src))" % (d, el.S.degree),
                 "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
-                "traffic": profiled_traffic(), "peak_source": peak_src,
+                "traffic": profiled_traffic() if args.workload == "marmousi" and dev.symmetric else None,
+                "peak_source": peak_src,
                 "alg_bytes_per_launch": dom["alg_bytes"], "ms_per_launch": dom["ms"],
                 "moved_bytes_per_launch": dom["moved_bytes"], "moved_gbs": dom["moved_gbs"],
                 "moved_frac": dom["moved_gbs"] / peak,
-                "note": "achieved/frac use the ALGORITHMIC bytes of SURVEY.md 8d (full d*d stress: 14*nd*8 B per cell "
+                "note": "achieved/frac use the ALGORITHMIC bytes of SURVEY.md 8d (full d*d stress: %d*nd*8 B per cell "
                         "for K6); with symmetric stress storage the kernel moves only moved_bytes_per_launch "
-                        "(11*nd*8 B per cell), so frac can exceed moved_frac -- moved_frac is the kernel's real "
-                        "HBM efficiency, frac the speed-up-relevant one"}
+                        "(%d*nd*8 B per cell), so frac can exceed moved_frac -- moved_frac is the kernel's real "
+                        "HBM efficiency, frac the speed-up-relevant one" % (cell_doubles[6], moved_doubles[6])}
     step_gbs = 64.0 * ndof_local * K / (ms_local * 1e-3) / 1e9
     moved_per_dof = 8.0 * sum(moved_doubles.values()) / (d + d * d)
     roofline_step = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
@@ -355,7 +380,7 @@ def run_gpu(args):
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.workload == "marmousi":
         co, u, s, cdt, cndof, sample = sample_problem()
         t1 = time_cpu(co, u, s, cdt, 1, 1)
         csteps = max(2, min(60, int(15.0 / max(t1, 1e-6))))
@@ -367,10 +392,12 @@ def run_gpu(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
-               "config": {"workload": wname, "degree": DEGREE, "dim": 2, "cells_per_gpu": int(E),
+               "config": {"workload": wname, "degree": int(el.S.degree), "dim": int(d), "cells_per_gpu": int(E),
                           "dof_per_gpu": int(ndof_local), "dof_total": int(ndof), "dt": dt,
-                          "material": "per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1",
-                          "source": "Ricker, one cell box per tile", "sponge": "none",
+                          "material": ("per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1"
+                                       if args.workload == "marmousi" else "constant lambda=0.5, mu=0.25, rho=1"),
+                          "source": "Ricker, one cell box per tile" if args.workload == "marmousi" else "none",
+                          "sponge": "none",
                           "initial_data": "random 1e-3 velocity, random 1e-3 symmetric stress",
                           "stress_storage": "symmetric (upper triangle)" if dev.symmetric else "full",
                           "l2": ("state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)"
@@ -395,6 +422,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="mesh resolution factor (development aid; 1 = headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="marmousi", choices=["marmousi", "box3d"],
+                    help="marmousi (default, the headline: BASELINE.json configs[3]); box3d: configs[4], 3D P3 weak scaling")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's scaling run): 53.4 M DoF per GPU; strong: 53.4 M DoF in total")
     args = ap.parse_args()

@@ -476,13 +476,26 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
 #pragma unroll
         for (int a = 0; a < ND; ++a)
           p.out[orow + (size_t)a * TILE] = fma(p.c0, a0[a * TILE], fma(p.c1, a1[a * TILE], p.c2 * acc[a]));
+      } else if (AXPY) {
+        // operands straight from global memory (L2-prefetched by issue_tile).  out aliases ax0 (u is updated in
+        // place), so the compiler may not move a load above an earlier store: load a batch first, then store it
+        constexpr int CH = 10;
+#pragma unroll
+        for (int a0 = 0; a0 < ND; a0 += CH) {
+          double x0[CH], x1[CH];
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (a0 + k < ND) {
+              x0[k] = p.ax0[orow + (size_t)(a0 + k) * TILE];
+              x1[k] = p.ax1[orow + (size_t)(a0 + k) * TILE];
+            }
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+            if (a0 + k < ND) p.out[orow + (size_t)(a0 + k) * TILE] = fma(p.c0, x0[k], fma(p.c1, x1[k], p.c2 * acc[a0 + k]));
+        }
       } else {
 #pragma unroll
-        for (int a = 0; a < ND; ++a) {
-          double v = acc[a];
-          if (AXPY) v = fma(p.c0, p.ax0[orow + (size_t)a * TILE], fma(p.c1, p.ax1[orow + (size_t)a * TILE], p.c2 * v));
-          p.out[orow + (size_t)a * TILE] = v;
-        }
+        for (int a = 0; a < ND; ++a) p.out[orow + (size_t)a * TILE] = acc[a];
       }
     };
     if (ROWS_FIRST) {
@@ -590,8 +603,26 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
 #pragma unroll
     for (int ii = 0; ii < IPT; ++ii) {
       const int i = ig * IPT + ii;
+      // AXPY operands straight from global memory (large elements; L2-prefetched by issue_tile): out aliases ax0
+      // (s is updated in place), so the compiler may not move a load above an earlier store -- load the operands of
+      // CH nodes first, then compute and store them
+      constexpr bool DIRECT = AXPY && !AXS;
+      constexpr int CH = 5;
+      double x0[DIRECT ? CH : 1][D], x1[DIRECT ? CH : 1][D];
 #pragma unroll
       for (int a = 0; a < ND; ++a) {
+        if (DIRECT && a % CH == 0) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) {
+              const int j = SYM ? (i + jj) % D : jj;
+              if (a + k >= ND || (SYM && !(D == 2 ? (jj == 0 || i == 0) : (jj < 2)))) continue;
+              const size_t og = (size_t)tile * (KS * TILE) + (scomp<D, SYM>(i, j) * ND + a + k) * TILE + lane;
+              x0[DIRECT ? k : 0][jj] = p.ax0[og];
+              x1[DIRECT ? k : 0][jj] = p.ax1[og];
+            }
+        }
         double div = XREG ? XR[a] : X[(0 * ND + a) * TILE];
 #pragma unroll
         for (int k = 1; k < D; ++k) div += XREG ? XR[(k * D + k) * ND + a] : X[((k * D + k) * ND + a) * TILE];
@@ -610,8 +641,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
             const double* a1 = reinterpret_cast<const double*>(stage + pl.ax1);
             v = fma(p.c0, a0[o], fma(p.c1, a1[o], p.c2 * v));
           } else if (AXPY) {
-            const size_t og = (size_t)tile * (KS * TILE) + o;
-            v = fma(p.c0, p.ax0[og], fma(p.c1, p.ax1[og], p.c2 * v));
+            v = fma(p.c0, x0[DIRECT ? a % CH : 0][jj], fma(p.c1, x1[DIRECT ? a % CH : 0][jj], p.c2 * v));
           }
           out[o] = v;
         }
