@@ -292,6 +292,13 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
     int grid = h->nsm * *occ;
     const int cap = env_int("SG_GRID_PER_SM");
     if (cap > 0) grid = h->nsm * cap;
+    // experiment for the next round (off by default, unmeasured): leave room for the boundary kernel's CTAs next to
+    // the persistent interior grid, so that boundary(k+1) + exchange overlap interior(k+1) instead of trailing it
+    // (3D P3 at N = 2 loses 42 us per pass to that chain: profiles/README.md)
+    if (part == SG_PART_INTERIOR && h->npeers > 0 && env_int("SG_INTERIOR_RESERVE") > 0) {
+      const int reserve = std::min(h->tiles_boundary, grid / 4);
+      grid -= reserve;
+    }
     if (grid > nt) grid = nt;
     void* args[] = {(void*)&p};
     SG_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(nthreads), args, pl.total, st));
@@ -454,7 +461,16 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   } while (0)
 
   SG_CUDA_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  SG_CUDA_H(cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+  {
+    // the comm stream carries the boundary tiles and the halo exchange of every pass: highest priority, so that when
+    // boundary(k+1) and interior(k+1) become ready together the boundary CTAs are dispatched first and the
+    // push/signal/wait chain overlaps the interior kernel instead of trailing it (kernel nodes captured from this
+    // stream keep the priority inside the step graph)
+    int least = 0, greatest = 0;
+    SG_CUDA_H(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const int prio = env_int("SG_COMM_PRIORITY_OFF") ? least : greatest;
+    SG_CUDA_H(cudaStreamCreateWithPriority(&h->comm, cudaStreamNonBlocking, prio));
+  }
   SG_CUDA_H(cudaEventCreate(&h->ev0));
   SG_CUDA_H(cudaEventCreate(&h->ev1));
   SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
