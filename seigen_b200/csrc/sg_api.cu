@@ -1,6 +1,7 @@
 // C ABI (include/seigen_b200.h) over the fused sm_100a stage kernels.  No torch types, no CPU fallback.
 #include "../../include/seigen_b200.h"
 #include "sg_kernels.cuh"
+#include "sg_variants.h"
 
 #include <algorithm>
 #include <cmath>
@@ -28,79 +29,16 @@ int fail(int code, const std::string& msg) {
     }                                                                                          \
   } while (0)
 
-// ---- per-element kernel configuration ------------------------------------------------------
-struct Variant {
-  int dim, degree, nd, nfp, tile, split, minb, ns_plain, ns_axpy, axs;
-  // [0]: full stress storage (D*D components), [1]: symmetric storage (upper triangle)
-  sg::StagePlan (*plan_f[2])(bool classes, bool mat, bool sponge);
-  sg::StagePlan (*plan_f_axpy[2])(bool classes, bool mat, bool sponge);
-  sg::StagePlan (*plan_g[2])(bool classes, bool mat, bool sponge);
-  sg::StagePlan (*plan_g_axpy[2])(bool classes, bool mat, bool sponge);
-  const void* f_plain[2];
-  const void* f_axpy[2];
-  const void* g_plain[2];
-  const void* g_axpy[2];
-};
-
-// TILE cells per tile, SPLIT threads per cell, MINB / MINBA CTAs per SM the compiler must allow for the plain / AXPY
-// kernels (register cap), NSP / NSA pipeline depth of the plain / AXPY kernels, AXS: stage the AXPY operands through
-// shared memory (bulk copies) instead of reading them from L2, XREG: G-type gradients in registers (SPLIT == 1)
-template <int D, int P, int TILE, int SPLIT, int MINB, int MINBA, int NSP, int NSA, bool AXS, bool XREG, bool SYM>
-void fill_variant(Variant& v) {
-  using E = ElemOps<D, P>;
-  constexpr int m = SYM ? 1 : 0;
-  v.plan_f[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, false, false, false, SYM>(c, mt, sp, E::FTAB_SIZE); };
-  v.plan_f_axpy[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, false, AXS, false, SYM>(c, mt, sp, E::FTAB_SIZE); };
-  v.plan_g[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSP, true, false, !XREG, SYM>(c, mt, sp, E::FTAB_SIZE); };
-  v.plan_g_axpy[m] = [](bool c, bool mt, bool sp) { return sg::make_plan<D, E::ND, TILE, NSA, true, AXS, !XREG, SYM>(c, mt, sp, E::FTAB_SIZE); };
-  v.f_plain[m] = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false, SYM>;
-  v.f_axpy[m] = (const void*)&sg::stage_f_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS, SYM>;
-  v.g_plain[m] = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINB, NSP, false, false, XREG, SYM>;
-  v.g_axpy[m] = (const void*)&sg::stage_g_kernel<D, P, TILE, SPLIT, MINBA, NSA, true, AXS, XREG, SYM>;
-}
-
-template <int D, int P, int TILE, int SPLIT, int MINB, int MINBA, int NSP, int NSA, bool AXS, bool XREG>
-Variant make_variant() {
-  using E = ElemOps<D, P>;
-  Variant v;
-  v.dim = D;
-  v.degree = P;
-  v.nd = E::ND;
-  v.nfp = E::NFP;
-  v.tile = TILE;
-  v.split = SPLIT;
-  v.minb = MINB;
-  v.ns_plain = NSP;
-  v.ns_axpy = NSA;
-  v.axs = AXS;
-  fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, false>(v);
-  fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, true>(v);
-  return v;
-}
-
 const std::vector<Variant>& variants() {
-  static const std::vector<Variant> v = {
-      // first entry of each (dim, degree) is the default; the others are tuning candidates selectable with
-      // SG_TILE / SG_SPLIT / SG_MINB / SG_NS (scripts/perf_probe.py)
-      //            D  P  TILE SPLIT MINB MINBA NSP NSA AXS   XREG
-      make_variant<2, 1, 128, 1, 4, 2, 2, 2, true, true>(),
-      make_variant<2, 1, 64, 1, 8, 4, 2, 2, true, true>(),
-      make_variant<2, 2, 64, 1, 8, 3, 2, 2, true, true>(),
-      make_variant<2, 2, 64, 1, 10, 3, 2, 2, true, true>(),
-      make_variant<2, 2, 128, 1, 4, 2, 2, 2, true, true>(),
-      make_variant<2, 2, 64, 2, 4, 3, 2, 2, true, false>(),
-      make_variant<2, 3, 32, 1, 8, 4, 2, 2, true, true>(),
-      make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>(),
-      make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>(),
-      make_variant<3, 1, 64, 1, 4, 3, 2, 2, true, false>(),
-      make_variant<3, 1, 64, 1, 6, 3, 2, 2, true, false>(),
-      make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>(),
-      make_variant<3, 1, 32, 3, 4, 4, 3, 2, true, false>(),
-      make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>(),
-      make_variant<3, 2, 32, 3, 4, 4, 2, 2, true, false>(),
-      make_variant<3, 3, 32, 3, 2, 2, 2, 2, false, false>(),
-      make_variant<3, 3, 32, 3, 2, 2, 2, 1, false, false>(),
-  };
+  static const std::vector<Variant> v = [] {
+    std::vector<Variant> t;
+    sg_variants_2d_low(t);
+    sg_variants_2d_high(t);
+    sg_variants_3d_p1(t);
+    sg_variants_3d_p2(t);
+    sg_variants_3d_p3(t);
+    return t;
+  }();
   return v;
 }
 

@@ -1,0 +1,10 @@
+// Stage-kernel instantiations of one group of elements (see sg_variants.h).  First entry of each (dim, degree) is the
+// default; the others are tuning candidates selectable with SG_TILE / SG_SPLIT / SG_MINB / SG_NS (scripts/perf_probe.py).
+//                D  P  TILE SPLIT MINB MINBA NSP NSA AXS   XREG
+#define SG_STAGE_KERNELS_ONLY
+#include "sg_variants.h"
+
+void sg_variants_3d_p3(std::vector<Variant>& v) {
+  v.push_back(make_variant<3, 3, 32, 3, 2, 2, 2, 2, false, false>());
+  v.push_back(make_variant<3, 3, 32, 3, 2, 2, 2, 1, false, false>());
+}

@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
   if (tid == 0) sched_done(p.sched);
 }
 
+#ifndef SG_STAGE_KERNELS_ONLY   // the instantiation units (sg_inst_*.cu) only need the stage kernels
 // ---------------------------------------------------------------------------------------------
 // small utility kernels
 // ---------------------------------------------------------------------------------------------
@@ -811,5 +812,7 @@ __global__ void wait_kernel(unsigned long long* ctl, int npeers, long long timeo
   }
   __threadfence_system();
 }
+
+#endif  // SG_STAGE_KERNELS_ONLY
 
 }  // namespace sg
