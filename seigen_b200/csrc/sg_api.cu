@@ -239,7 +239,25 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
     }
     if (grid > nt) grid = nt;
     void* args[] = {(void*)&p};
-    SG_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(nthreads), args, pl.total, st));
+    if (part == SG_PART_BOUNDARY && env_int("SG_LAUNCH_PRIORITY") > 0) {
+      // experiment for the next round (off by default, unmeasured): give the boundary kernel node an explicit
+      // priority inside the captured graph instead of relying on the comm stream's
+      int least = 0, greatest = 0;
+      SG_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributePriority;
+      attr.val.priority = greatest;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(nthreads);
+      cfg.dynamicSmemBytes = pl.total;
+      cfg.stream = st;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      SG_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    } else {
+      SG_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(nthreads), args, pl.total, st));
+    }
   }
   return SG_OK;
 }
