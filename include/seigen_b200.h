@@ -111,6 +111,10 @@ int sg_get_field(sg_solver* h, int which, double* out);
 int sg_set_receivers(sg_solver* h, int64_t n, const int64_t* cell, const double* weights, int64_t max_steps);
 int sg_get_receivers(sg_solver* h, int64_t first_step, int64_t nsteps, double* out);
 
+/* For drivers that advance stage by stage with sg_stage (library transport, SG_HALO=nccl): record the receivers for
+ * 0-based step `step` now, on the compute stream -- what sg_step does itself after every step. */
+int sg_record_receivers(sg_solver* h, int64_t step);
+
 /* The loop body of ElasticLF4.run (elastic.py:283-304) `nsteps` times, starting at 0-based step index
  * `first_step` (only used to index the source table).  Work is queued on the solver's stream; the call
  * returns without waiting (sg_get_state / sg_synchronize wait). */
@@ -151,8 +155,12 @@ void* sg_field_ptr(sg_solver* h, int which);
  * that a library sends, each rank writes the rows of its cut-adjacent cells straight into the halo tiles of the
  * neighbouring ranks' fields through CUDA-IPC mappings (NVLink stores), then publishes an epoch flag in the
  * neighbour's memory; the consumer spins on its own flag.  With peers connected, sg_step replays ONE CUDA graph per
- * time step that contains all six passes and all six exchanges (boundary tiles -> push/signal/wait on the comm
- * stream, overlapped with the interior tiles) -- no host work and no library call inside a step.
+ * time step whose six stage kernels carry the six exchanges themselves: the CTAs that compute the tiles of the
+ * cut-adjacent cells (handed out first) wait for the peers' rows of the previous pass, store their own rows into the
+ * peers' halo tiles and publish the epoch, while the other CTAs are already on the interior tiles -- no host work,
+ * no library call, no extra kernel inside a step.  (SG_PEER_SCHED_SPLIT=1 selects the earlier two-stream schedule:
+ * boundary kernel -> push/signal/wait kernels on a comm stream next to the interior kernel.)
+ * SG_PEER_TIMEOUT_S bounds every device-side wait (default ~20 s).
  *   sg_ipc_export    5 handles of SG_IPC_HANDLE_BYTES bytes: u, s, uh, sh, control words
  *   sg_peer_connect  the handles of every neighbouring rank + where my cells land in its fields
  *   sg_exchange      one immediate exchange of field `which` on the compute stream (after sg_set_state)

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "sg_set_receivers": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64]),
     "sg_get_receivers": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "sg_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int64]),
+    "sg_record_receivers": (C.c_int, [_P, C.c_int64]),
     "sg_time_stage": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "sg_set_halo_plan": (C.c_int, [_P, C.c_int64, _P]),
     "sg_pack": (C.c_int, [_P, C.c_int, _P, C.c_int]),

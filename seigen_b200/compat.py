@@ -65,7 +65,9 @@ def mesh_plan(mesh: Mesh):
         rank, size = _dist()
         part = getattr(mesh, "_partition", None)
         if part is None:
-            part = partition_cells(mesh, size, getattr(mesh, "partition_method", "rcb"))
+            import os
+            method = os.environ.get("SG_PARTITION") or getattr(mesh, "partition_method", "rcb")
+            part = partition_cells(mesh, size, method)
             mesh._partition = part
         plan = build_rank_plan(mesh, part, rank, size)
         mesh._plan = plan
@@ -203,16 +205,34 @@ class Function:
 
 
 class File:
-    """``File("velocity.pvd")`` (elastic.py:123-124).  Writes legacy-VTK snapshots when ``write`` is called."""
+    """``File("velocity.pvd")`` (elastic.py:123-124).  Every ``write`` adds one snapshot ``<base>_<n>.vtu`` holding
+    all nd nodes of every owned cell (``vtkout.write_vtu``) and rewrites the ``.pvd`` collection, so the series can
+    be opened while the run is still going, as with Firedrake's File.  With several ranks each writes its own piece
+    ``<base>_<n>_<rank>.vtu`` and rank 0 adds the ``<base>_<n>.pvtu`` that ties them together (the reference's
+    parallel output) -- no two ranks ever write the same path."""
 
     def __init__(self, name):
         self.name = name
         self.count = 0
+        self.entries = []
 
     def write(self, f, time=None):
-        from .vtkout import write_vtk
+        from .vtkout import write_pvd, write_pvtu, write_vtu
         base = self.name.rsplit(".", 1)[0]
-        write_vtk(f"{base}_{self.count}.vtk", f)
+        rank, size = _dist()
+        t = float(self.count if time is None else time)
+        if size == 1:
+            snap = f"{base}_{self.count}.vtu"
+            write_vtu(snap, f)
+        else:
+            pieces = [f"{base}_{self.count}_{r}.vtu" for r in range(size)]
+            name, nc = write_vtu(pieces[rank], f)
+            snap = f"{base}_{self.count}.pvtu"
+            if rank == 0:
+                write_pvtu(snap, pieces, name, nc)
+        self.entries.append((t, snap))
+        if rank == 0:
+            write_pvd(base + ".pvd", self.entries)
         self.count += 1
 
     def __lshift__(self, f):

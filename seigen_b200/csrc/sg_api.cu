@@ -98,7 +98,7 @@ struct sg_solver {
   DevBuf<int64_t> rec_cell;               // receivers: owning cell, basis weights, samples [max_steps][nrec][dim]
   DevBuf<double> rec_w, rec_data;
   int64_t nrec = 0, rec_steps = 0;
-  DevBuf<unsigned int> sched;             // [3 parts][2] dynamic tile scheduler words (sg::sched_next)
+  DevBuf<unsigned int> sched;             // [3 parts][4] dynamic tile scheduler words (sg::sched_next, sg::halo_push)
   int nsm = 148;
   int occ[4] = {0, 0, 0, 0};            // resident CTAs per SM of f_plain, f_axpy, g_plain, g_axpy
   uint32_t occ_smem[4] = {0, 0, 0, 0};  // the shared-memory size those were computed for
@@ -115,6 +115,11 @@ struct sg_solver {
   DevBuf<int32_t> send_peer;                 // [nsend] index into the peer tables
   DevBuf<double*> rfield;                    // [4][npeers] peers' u, s, uh, sh
   DevBuf<unsigned long long*> rflag;         // [npeers] my flag slot in each peer's ctl
+  // the same send list regrouped by boundary tile for the exchange fused into the stage kernels (sg::halo_push)
+  DevBuf<int32_t> push_start, push_lane, push_peer;
+  DevBuf<int64_t> push_dst;
+  int push_tiles = 0;
+  long long timeout_cycles = (long long)40e9;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_int[6] = {}, ev_bnd[6] = {};
   // CUDA graph of one time step
   cudaGraphExec_t graph = nullptr;
@@ -156,7 +161,10 @@ sg::StageParams base_params(sg_solver* h) {
   return p;
 }
 
-int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) {
+int field_ncomp(sg_solver* h, int which);
+const int STAGE_OUTPUT[7] = {-1, SG_FIELD_UH, SG_FIELD_SH, SG_FIELD_U, SG_FIELD_SH, SG_FIELD_UH, SG_FIELD_S};
+
+int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, bool push = false) {
   int t0 = 0, nt = h->tiles_owned;
   if (part == SG_PART_BOUNDARY) {
     nt = h->tiles_boundary;
@@ -170,7 +178,7 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
   sg::StageParams p = base_params(h);
   p.tile0 = t0;
   p.ntiles = nt;
-  p.sched = h->sched.p + 2 * part;
+  p.sched = h->sched.p + 4 * part;
   const double c3 = dt * dt * dt / 24.0;
   const bool classes = h->geoidx.p != nullptr, sponge = p.absidx != nullptr, mat = p.mat != nullptr;
   const void* fn = nullptr;
@@ -215,6 +223,21 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st) 
     p.step = h->step_dev.p;
     p.nsteps = h->src_steps;
     p.nsrc = h->nsrc;
+  }
+  if (push && h->npeers > 0 && h->push_tiles > 0) {
+    // halo exchange of this pass's output fused into the kernel (sg::halo_wait / sg::halo_push)
+    const int which = STAGE_OUTPUT[stage];
+    p.push_tiles = h->push_tiles;
+    p.npeers = h->npeers;
+    p.K_out = field_ncomp(h, which) * h->nd;
+    p.push_start = h->push_start.p;
+    p.push_lane = h->push_lane.p;
+    p.push_peer = h->push_peer.p;
+    p.push_dst = h->push_dst.p;
+    p.rfield = h->rfield.p + (size_t)which * h->npeers;
+    p.ctl = h->ctl.p;
+    p.rflag = h->rflag.p;
+    p.timeout_cycles = h->timeout_cycles;
   }
   if (nt > 0) {
     const int nthreads = v->tile * v->split;
@@ -279,7 +302,6 @@ int relayout(sg_solver* h, double* dev, double* host_order, int ncomp, bool to_d
 }
 
 DevBuf<double>* field_buf(sg_solver* h, int which);
-int field_ncomp(sg_solver* h, int which);
 int field_ncomp_boundary(sg_solver* h, int which);
 
 // push my cut-adjacent cells of field `which` into the peers' halo tiles, publish, then wait for the peers' rows
@@ -293,14 +315,13 @@ int enqueue_exchange(sg_solver* h, int which, cudaStream_t st) {
   SG_CUDA(cudaGetLastError());
   sg::signal_kernel<<<1, 32, 0, st>>>(h->ctl.p, h->rflag.p, h->npeers);
   SG_CUDA(cudaGetLastError());
-  sg::wait_kernel<<<1, 32, 0, st>>>(h->ctl.p, h->npeers, (long long)40e9);
+  sg::wait_kernel<<<1, 32, 0, st>>>(h->ctl.p, h->npeers, h->timeout_cycles);
   SG_CUDA(cudaGetLastError());
   return SG_OK;
 }
 
-const int STAGE_OUTPUT[7] = {-1, SG_FIELD_UH, SG_FIELD_SH, SG_FIELD_U, SG_FIELD_SH, SG_FIELD_UH, SG_FIELD_S};
-
-// One time step on a rank with peers: two chains that only meet where the data says they must.
+// One time step on a rank with peers, two-stream schedule (SG_PEER_SCHED=split; the default is the fused schedule
+// below): two chains that only meet where the data says they must.
 //   compute stream:  interior(1) -> interior(2) -> ... -> interior(6)
 //   comm stream:     boundary(1) -> push/signal/wait -> boundary(2) -> push/signal/wait -> ...
 // interior(k+1) needs boundary(k) (it reads cut-adjacent neighbours) but never the halo, so the exchange latency is
@@ -326,6 +347,20 @@ int enqueue_step_peers(sg_solver* h, double dt) {
   }
   SG_CUDA(cudaEventRecord(h->ev_join, cm));
   SG_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+  return SG_OK;
+}
+
+// One time step on a rank with peers, fused schedule: six launches over ALL owned tiles, exactly the single-GPU
+// step.  The tiles of the cut-adjacent cells come first in the tile order, so the persistent CTAs take them first;
+// each of them waits (device-side flag) for the peers' rows of the previous pass, computes, stores its cells' rows
+// into the peers' halo tiles over NVLink and the last one publishes the epoch -- all while the other CTAs are
+// already working through the interior tiles.  No second stream, no events, no extra kernels: the exchange costs
+// nothing on the critical path unless a peer is late.
+int enqueue_step_fused(sg_solver* h, double dt) {
+  for (int k = 1; k <= 6; ++k) {
+    int rc = launch_stage(h, k, SG_PART_ALL, dt, h->stream, true);
+    if (rc) return rc;
+  }
   return SG_OK;
 }
 
@@ -436,8 +471,12 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
     SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_int[k], cudaEventDisableTiming));
     SG_CUDA_H(cudaEventCreateWithFlags(&h->ev_bnd[k], cudaEventDisableTiming));
   }
-  SG_CUDA_H(h->sched.alloc(8));
-  SG_CUDA_H(cudaMemsetAsync(h->sched.p, 0, 8 * sizeof(unsigned int), h->stream));
+  SG_CUDA_H(h->sched.alloc(12));
+  SG_CUDA_H(cudaMemsetAsync(h->sched.p, 0, 12 * sizeof(unsigned int), h->stream));
+  if (const char* e = std::getenv("SG_PEER_TIMEOUT_S")) {
+    const double sec = std::atof(e);
+    if (sec > 0) h->timeout_cycles = (long long)(sec * 1.9e9);   // clock64 ticks at ~1.9 GHz
+  }
   SG_CUDA_H(h->ctl.alloc(sg::SG_CTL_WORDS));
   SG_CUDA_H(cudaMemsetAsync(h->ctl.p, 0, sg::SG_CTL_WORDS * 8, h->stream));
 
@@ -577,6 +616,7 @@ void sg_destroy(sg_solver* h) {
   h->rec_cell.release(); h->rec_w.release(); h->rec_data.release();
   h->asym.release();
   h->sched.release(); h->ctl.release(); h->send_dst.release(); h->send_peer.release(); h->rfield.release(); h->rflag.release();
+  h->push_start.release(); h->push_lane.release(); h->push_peer.release(); h->push_dst.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->comm) cudaStreamDestroy(h->comm);
   delete h;
@@ -813,8 +853,10 @@ int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
     cudaGraph_t g = nullptr;
     SG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = SG_OK;
-    if (h->npeers > 0)
+    if (h->npeers > 0 && env_int("SG_PEER_SCHED_SPLIT") > 0)
       rc = enqueue_step_peers(h, dt);
+    else if (h->npeers > 0)
+      rc = enqueue_step_fused(h, dt);
     else
       for (int k = 1; k <= 6 && rc == SG_OK; ++k) rc = launch_stage(h, k, SG_PART_ALL, dt, st);
     if (rc == SG_OK && h->nrec > 0)
@@ -908,6 +950,18 @@ int sg_get_receivers(sg_solver* h, int64_t first_step, int64_t nsteps, double* o
   SG_CUDA(cudaMemcpyAsync(out, h->rec_data.p + (size_t)first_step * row, (size_t)nsteps * row * 8,
                           cudaMemcpyDeviceToHost, h->stream));
   SG_CUDA(cudaStreamSynchronize(h->stream));
+  return SG_OK;
+}
+
+int sg_record_receivers(sg_solver* h, int64_t step) {
+  if (!h) return fail(SG_EINVAL, "null solver");
+  if (h->nrec == 0) return SG_OK;
+  SG_CUDA(cudaSetDevice(h->device));
+  sg::set_step_kernel<<<1, 1, 0, h->stream>>>(h->step_dev.p, step);
+  SG_CUDA(cudaGetLastError());
+  sg::receivers_kernel<<<1, 128, 0, h->stream>>>(h->u.p, h->rec_cell.p, h->rec_w.p, h->rec_data.p, h->step_dev.p,
+                                                 h->rec_steps, (int)h->nrec, h->nd, h->dim, h->tile);
+  SG_CUDA(cudaGetLastError());
   return SG_OK;
 }
 
@@ -1036,6 +1090,45 @@ int sg_peer_connect(sg_solver* h, int32_t npeers, const sg_peer_desc* peers) {
   }
   for (int64_t k = 0; k < h->nsend; ++k)
     if (who[(size_t)k] < 0) return fail(SG_EINVAL, "sg_peer_connect: a send cell has no destination");
+  // the send list regrouped by (tile, peer, remote cell) for the fused exchange; needs the send cells on the host
+  {
+    std::vector<int64_t> cells((size_t)h->nsend);
+    if (h->nsend) SG_CUDA(cudaMemcpy(cells.data(), h->send_cells.p, (size_t)h->nsend * 8, cudaMemcpyDeviceToHost));
+    const int T = h->tile;
+    h->push_tiles = h->tiles_boundary;
+    std::vector<int64_t> order((size_t)h->nsend);
+    for (int64_t k = 0; k < h->nsend; ++k) {
+      order[(size_t)k] = k;
+      if (cells[(size_t)k] / T >= h->tiles_boundary)
+        return fail(SG_EINVAL, "sg_peer_connect: a send cell lies outside the boundary tiles (n_boundary too small)");
+    }
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      const int64_t ta = cells[(size_t)a] / T, tb = cells[(size_t)b] / T;
+      if (ta != tb) return ta < tb;
+      if (who[(size_t)a] != who[(size_t)b]) return who[(size_t)a] < who[(size_t)b];
+      return dst[(size_t)a] < dst[(size_t)b];
+    });
+    std::vector<int32_t> pstart((size_t)h->push_tiles + 1, 0), plane((size_t)h->nsend), ppeer((size_t)h->nsend);
+    std::vector<int64_t> pdst((size_t)h->nsend);
+    for (int64_t i = 0; i < h->nsend; ++i) {
+      const int64_t k = order[(size_t)i];
+      pstart[(size_t)(cells[(size_t)k] / T) + 1]++;
+      plane[(size_t)i] = (int32_t)(cells[(size_t)k] % T);
+      ppeer[(size_t)i] = who[(size_t)k];
+      pdst[(size_t)i] = dst[(size_t)k];
+    }
+    for (int t = 0; t < h->push_tiles; ++t) pstart[(size_t)t + 1] += pstart[(size_t)t];
+    SG_CUDA(h->push_start.alloc(pstart.size()));
+    SG_CUDA(h->push_lane.alloc(std::max<size_t>(plane.size(), 1)));
+    SG_CUDA(h->push_peer.alloc(std::max<size_t>(ppeer.size(), 1)));
+    SG_CUDA(h->push_dst.alloc(std::max<size_t>(pdst.size(), 1)));
+    SG_CUDA(cudaMemcpy(h->push_start.p, pstart.data(), pstart.size() * 4, cudaMemcpyHostToDevice));
+    if (h->nsend) {
+      SG_CUDA(cudaMemcpy(h->push_lane.p, plane.data(), plane.size() * 4, cudaMemcpyHostToDevice));
+      SG_CUDA(cudaMemcpy(h->push_peer.p, ppeer.data(), ppeer.size() * 4, cudaMemcpyHostToDevice));
+      SG_CUDA(cudaMemcpy(h->push_dst.p, pdst.data(), pdst.size() * 8, cudaMemcpyHostToDevice));
+    }
+  }
   SG_CUDA(h->rfield.alloc(rf.size()));
   SG_CUDA(h->rflag.alloc(fl.size()));
   SG_CUDA(h->send_dst.alloc(dst.size()));

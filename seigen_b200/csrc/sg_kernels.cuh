@@ -54,7 +54,24 @@ struct StageParams {
   double src_scale;
   int32_t tile0;          // first tile of this launch
   int32_t ntiles;         // tiles of this launch
-  unsigned int* sched;    // [2] dynamic tile scheduler of this launch: next ticket, CTAs finished (both 0 at launch)
+  unsigned int* sched;    // [4] dynamic tile scheduler of this launch: next ticket, CTAs finished, boundary tiles
+                          // pushed (all 0 at launch)
+  // Halo exchange fused into the pass (one process per GPU, peers' fields mapped through CUDA IPC).  Tiles
+  // [0, push_tiles) hold the cut-adjacent cells: they are handed out first, the CTA that computes one waits for the
+  // peers' rows of the previous exchange before it reads a halo cell, and afterwards stores the rows of its
+  // cut-adjacent cells straight into the peers' halo tiles; whoever finishes the last of these tiles publishes the
+  // new epoch to every peer.  push_tiles = 0: no exchange in this launch.
+  int32_t push_tiles;
+  int32_t npeers;
+  int32_t K_out;                        // rows per cell of the output field
+  const int32_t* push_start;            // [push_tiles + 1] first entry of each tile
+  const int32_t* push_lane;             // [n] lane of the cell inside its tile
+  const int32_t* push_peer;             // [n] index into rfield / rflag
+  const int64_t* push_dst;              // [n] device cell index in the peer's copy of the field
+  double* const* rfield;                // [npeers] the peers' copy of the output field
+  unsigned long long* ctl;              // my control words (SG_CTL_*)
+  unsigned long long* const* rflag;     // [npeers] my flag slot in each peer's control words
+  long long timeout_cycles;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -400,6 +417,74 @@ __device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan&
   if (NS == 1) __syncthreads();
 
 // ---------------------------------------------------------------------------------------------
+// Halo exchange inside a pass (StageParams::push_*).  ctl layout (uint64): [0, 16) flags written by my peers,
+// [16] exchanges I have published, [18] error word (1 = a wait timed out).  Every rank issues the same sequence of
+// exchanges, so "the peers' rows of the previous exchange have landed" == flag[p] >= number of exchanges I have
+// published myself.
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_CTL_SENT = 16, SG_CTL_ERROR = 18, SG_CTL_WORDS = 32;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Spin (bounded) until flag slot `slot` of ctl has reached `epoch`; raises the error word instead of hanging.
+__device__ __forceinline__ void wait_flag(unsigned long long* ctl, int slot, unsigned long long epoch,
+                                          long long timeout_cycles) {
+  const unsigned long long* f = ctl + slot;
+  if (ld_acquire_sys(f) >= epoch) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(f) < epoch) {
+    if (clock64() - t0 > timeout_cycles) {
+      ctl[SG_CTL_ERROR] = 1;
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+
+// Before a CTA reads halo cells: the peers' rows of the last exchange must have landed.  Called by all threads.
+__device__ __forceinline__ void halo_wait(const StageParams& p) {
+  if ((int)threadIdx.x < p.npeers) {
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(p.ctl + SG_CTL_SENT);
+    wait_flag(p.ctl, threadIdx.x, epoch, p.timeout_cycles);
+  }
+  __syncthreads();
+}
+
+// After a CTA has stored boundary tile `tile` (and synchronised): copy the rows of its cut-adjacent cells into the
+// peers' halo tiles (entries sorted by peer and remote cell: consecutive threads write consecutive remote lanes),
+// then count the tile; the CTA that completes the last one publishes the epoch.  Called by all threads.
+template <int TILE, int NT>
+__device__ __forceinline__ void halo_push(const StageParams& p, int tile) {
+  const int lo = p.push_start[tile], n = p.push_start[tile + 1] - lo;
+  const int K = p.K_out;
+  const double* src = p.out + (size_t)tile * K * TILE;
+  for (int idx = threadIdx.x; idx < n * K; idx += NT) {
+    const int c = lo + idx % n, k = idx / n;
+    const int64_t r = p.push_dst[c];
+    double* dst = p.rfield[p.push_peer[c]];
+    dst[((r / TILE) * K + k) * TILE + r % TILE] = src[k * TILE + p.push_lane[c]];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                   // this CTA's remote rows before the count / the flag
+    if (atomicAdd(p.sched + 2, 1u) == (unsigned)p.push_tiles - 1u) {
+      p.sched[2] = 0u;
+      __threadfence_system();
+      const unsigned long long epoch = p.ctl[SG_CTL_SENT] + 1;
+      p.ctl[SG_CTL_SENT] = epoch;
+      for (int q = 0; q < p.npeers; ++q) st_release_sys(p.rflag[q], epoch);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // F-type pass:   out_i = Dv(in)_i - A_cell * absu_i            (K1, K5)
 //                out_i = c0*ax0_i + c1*ax1_i + c2*(Dv(in)_i - A_cell*absu_i)   (K3, AXPY)
 // Persistent CTAs with a dynamic tile scheduler; the bulk copies of the next NS-1 tiles are in flight while a
@@ -428,6 +513,8 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     const int tile = p.tile0 + t;
     unsigned char* stage = smem + slot * pl.stage_bytes;
     const double* sIn = reinterpret_cast<const double*>(stage + pl.in);
+    const bool btile = tile < p.push_tiles;
+    if (btile) halo_wait(p);
     mbar_wait(bars + slot, (it / NS) & 1);
 
     FaceGeom<D, ND, NFP, TILE> g;
@@ -515,6 +602,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
       }
     }
     __syncthreads();   // the stage may be refilled from the next iteration on
+    if (btile) halo_push<TILE, NT>(p, tile);
   }
   if (tid == 0) sched_done(p.sched);
 }
@@ -554,6 +642,8 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
     }
     unsigned char* stage = smem + slot * pl.stage_bytes;
     const double* sIn = reinterpret_cast<const double*>(stage + pl.in);
+    const bool btile = tile < p.push_tiles;
+    if (btile) halo_wait(p);
     mbar_wait(bars + slot, (it / NS) & 1);
 
     FaceGeom<D, ND, NFP, TILE> g;
@@ -652,6 +742,10 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
       const int64_t st = *p.step;
       if (st >= 0 && st < p.nsteps)
         for (int k = s_lo + tid; k < s_hi; k += NT) out[p.src_off[k]] += p.src_scale * p.amp[st * p.nsrc + k];
+    }
+    if (btile) {
+      __syncthreads();   // source values are part of what travels
+      halo_push<TILE, NT>(p, tile);
     }
   }
   if (tid == 0) sched_done(p.sched);
@@ -767,10 +861,7 @@ __global__ void push_kernel(const double* __restrict__ field, const int64_t* __r
   }
 }
 
-// ctl layout (uint64): [0, 16) flags written by my peers, [16] exchanges I have signalled, [17] exchanges I have
-// waited for, [18] error word (1 = a wait timed out)
-constexpr int SG_CTL_SENT = 16, SG_CTL_WAITED = 17, SG_CTL_ERROR = 18, SG_CTL_WORDS = 32;
-
+// Stand-alone exchange (sg_exchange: after sg_set_state, and the two-stream schedule kept for comparison).
 // After push_kernel (stream order): make the pushed rows visible system-wide, then publish the new epoch in every
 // peer's flag slot for me.
 __global__ void signal_kernel(unsigned long long* ctl, unsigned long long* const* __restrict__ rflag, int npeers) {
@@ -781,35 +872,13 @@ __global__ void signal_kernel(unsigned long long* ctl, unsigned long long* const
   }
   __syncthreads();
   __threadfence_system();
-  if ((int)threadIdx.x < npeers) {
-    unsigned long long* f = rflag[threadIdx.x];
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
-  }
+  if ((int)threadIdx.x < npeers) st_release_sys(rflag[threadIdx.x], epoch);
 }
 
-// Spins until every peer has published the epoch this rank is about to consume (bounded: sets the error word
-// instead of hanging if a peer never arrives).
+// Spins until every peer has published as many exchanges as this rank has (bounded: sets the error word instead of
+// hanging if a peer never arrives).
 __global__ void wait_kernel(unsigned long long* ctl, int npeers, long long timeout_cycles) {
-  __shared__ unsigned long long epoch;
-  if (threadIdx.x == 0) {
-    epoch = ctl[SG_CTL_WAITED] + 1;
-    ctl[SG_CTL_WAITED] = epoch;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < npeers) {
-    const unsigned long long* f = ctl + threadIdx.x;
-    const long long t0 = clock64();
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (v >= epoch) break;
-      if (clock64() - t0 > timeout_cycles) {
-        ctl[SG_CTL_ERROR] = 1;
-        break;
-      }
-      __nanosleep(200);
-    } while (true);
-  }
+  if ((int)threadIdx.x < npeers) wait_flag(ctl, threadIdx.x, ctl[SG_CTL_SENT], timeout_cycles);
   __threadfence_system();
 }
 

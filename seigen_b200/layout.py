@@ -25,18 +25,24 @@ from .mesh import BOUNDARY, Mesh, Topology
 __all__ = ["hilbert_key", "hilbert_order", "partition_cells", "RankPlan", "build_rank_plan"]
 
 
-def hilbert_key(points: np.ndarray, bits: int | None = None) -> np.ndarray:
-    """Hilbert-curve index (uint64) of each point (n, d); Skilling's transpose algorithm, vectorised."""
+def hilbert_key(points: np.ndarray, bits: int | None = None, bbox=None) -> np.ndarray:
+    """Hilbert-curve index (uint64) of each point (n, d); Skilling's transpose algorithm, vectorised.  ``bbox`` =
+    (lo, hi) fixes the box the curve fills (default: the points' own bounding box); ranks that pass the same box get
+    the same key for the same point, whatever subset of the mesh they hold."""
     pts = np.asarray(points, dtype=np.float64)
     n, d = pts.shape
     if bits is None:
         bits = 63 // d if d > 1 else 62
         bits = min(bits, 20)
-    lo = pts.min(axis=0)
-    span = pts.max(axis=0) - lo
-    span[span == 0] = 1.0
+    if bbox is None:
+        lo = pts.min(axis=0)
+        span = pts.max(axis=0) - lo
+    else:
+        lo = np.asarray(bbox[0], dtype=np.float64)
+        span = np.asarray(bbox[1], dtype=np.float64) - lo
+    span = np.where(span == 0, 1.0, span)
     scale = ((1 << bits) - 1) / span.max()
-    X = np.floor((pts - lo) * scale).astype(np.uint64).T.copy()      # (d, n)
+    X = np.clip(np.floor((pts - lo) * scale), 0, (1 << bits) - 1).astype(np.uint64).T.copy()      # (d, n)
     if d == 1:
         return X[0]
     M = np.uint64(1 << (bits - 1))
@@ -152,18 +158,22 @@ def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> Ran
     remote = spart[nb] != rank                                        # exterior facets point to self
     is_bnd = remote.any(axis=1)
 
-    key = hilbert_key(cent)
+    # one curve for all ranks (the mesh's bounding box): a rank's cut-adjacent cells and the halo copies its
+    # neighbours hold of them are then sorted alike, so a tile's rows land on consecutive halo lanes (coalesced
+    # NVLink stores in sg::halo_push)
+    key = hilbert_key(cent, bbox=(mesh.coords.min(axis=0), mesh.coords.max(axis=0)))
     o_b = owned[is_bnd]
     o_i = owned[~is_bnd]
     o_b = o_b[np.argsort(key[o_b], kind="stable")]
     o_i = o_i[np.argsort(key[o_i], kind="stable")]
     owned_sorted = np.concatenate([o_b, o_i])
 
-    # halo: remote cells across a facet of an owned cell, grouped by owner, ascending global id inside a group
-    # (sub-mesh indices ascend with global ids, so every rank derives the same order)
+    # halo: remote cells across a facet of an owned cell, grouped by owner, inside a group in the owner's own order of
+    # its cut-adjacent cells = (Hilbert key, global id)  (sub-mesh indices ascend with global ids, so every rank
+    # derives the same order)
     halo_ids = np.unique(nb[remote])
     halo_owner = spart[halo_ids]
-    order = np.lexsort((halo_ids, halo_owner))
+    order = np.lexsort((halo_ids, key[halo_ids], halo_owner))
     halo_ids, halo_owner = halo_ids[order], halo_owner[order]
     recv = {}
     for q in np.unique(halo_owner):
@@ -180,11 +190,11 @@ def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> Ran
     jinv = np.ascontiguousarray(topo.jinv[owned_sorted])
 
     # send lists: my cells that peer q sees across its facets = my cut-adjacent cells with a neighbour owned by q,
-    # in ascending global id (the order q's halo group uses)
+    # in (Hilbert key, global id) order = my own local order = the order q's halo group uses
     send, send_offsets, chunks, off = {}, {}, [], 0
     pb = spart[topo.nbr[o_b]]
     for q in sorted(recv):
-        mine = np.unique(o_b[(pb == q).any(axis=1)])
+        mine = o_b[(pb == q).any(axis=1)]                              # o_b is sorted by (key, global id) already
         loc = s2l[mine]
         send[q] = loc
         send_offsets[q] = (off, len(loc))

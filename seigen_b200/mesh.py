@@ -63,9 +63,16 @@ class Mesh:
     tests/explosive_source/src/domain.geo)."""
 
     def __init__(self, coords, cells=None, name="mesh", dim=None):
+        #: how the cells are split over ranks (layout.partition_cells): "rcb" (coordinate bisection: planes, optimal
+        #: for the structured utility meshes) or "metis" (graph partitioner on the dual graph; the default for
+        #: unstructured meshes read from a file when libsg_metis.so is built).  SG_PARTITION overrides both.
+        self.partition_method = "rcb"
         if isinstance(coords, (str, bytes)) or hasattr(coords, "__fspath__"):
             name = str(coords)
             coords, cells = read_gmsh(coords, dim=dim)
+            from . import partition_metis
+            if partition_metis.available():
+                self.partition_method = "metis"
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         if coords.ndim == 1:
             coords = coords[:, None]
