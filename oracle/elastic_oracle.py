@@ -185,7 +185,9 @@ class ElasticOracle:
     reshaped as ``(E, nd, d)`` / ``(E, nd, d, d)``).
     """
 
-    def __init__(self, coords, cells, degree, sigma_degree=None):
+    def __init__(self, coords, cells, degree, sigma_degree=None, lite=False):
+        """``lite``: skip the per-cell tables only the NumPy assembly needs (``gphi``: E*nq*nd*d doubles, 10 GB for
+        98 304 P3 tetrahedra); enough for the C restatement (``c_oracle.COracle``), which recomputes them per cell."""
         coords = np.asarray(coords, dtype=float)
         if coords.ndim == 1:
             coords = coords[:, None]
@@ -209,7 +211,7 @@ class ElasticOracle:
         self.detJ = np.abs(np.linalg.det(self.J))
         self.Jinv = np.linalg.inv(self.J)             # Jinv[e, r, k]
         # physical gradients of the basis at quadrature points: gphi[e, q, a, k]
-        self.gphi = np.einsum("qar,erk->eqak", self.dphi, self.Jinv)
+        self.gphi = None if lite else np.einsum("qar,erk->eqak", self.dphi, self.Jinv)
 
         # mass blocks and their inverses  (assemble(inner(w,u)*dx, inverse=True))
         Mref = np.einsum("q,qa,qb->ab", self.wq, self.phi, self.phi)

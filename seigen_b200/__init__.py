@@ -11,6 +11,7 @@ from .compat import (File, Function, FunctionSpace, TensorFunctionSpace, VectorF
                      errornorm_l2, get_timers, norm, timed_region)
 from .elastic import ElasticLF4, ExplicitElasticLF4, step_times  # noqa: F401
 from .expression import Expression  # noqa: F401
+from .forms import TestFunction, TrialFunction, dx, inner, lhs, rhs, solve  # noqa: F401
 from .helpers import Vp, Vs, cfl_dt, get_dofs, log  # noqa: F401
 from .mesh import (BoxMesh, IntervalMesh, Mesh, RectangleMesh, UnitCubeMesh, UnitIntervalMesh,  # noqa: F401
                    UnitSquareMesh)

@@ -203,6 +203,23 @@ class Function:
     def copy(self, deepcopy=True):
         return Function(self._fs, val=self.dat.data.copy(), name=self._name)
 
+    # pointwise expressions for the post-processing forms of the reference's scripts (forms.py): u1 - uexact, abs(..)
+    def __sub__(self, other):
+        from .forms import as_field
+        return as_field(self) - other
+
+    def __add__(self, other):
+        from .forms import as_field
+        return as_field(self) + other
+
+    def __neg__(self):
+        from .forms import as_field
+        return -as_field(self)
+
+    def __abs__(self):
+        from .forms import as_field
+        return abs(as_field(self))
+
 
 class File:
     """``File("velocity.pvd")`` (elastic.py:123-124).  Every ``write`` adds one snapshot ``<base>_<n>.vtu`` holding

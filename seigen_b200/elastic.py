@@ -142,6 +142,7 @@ class ExplicitElasticLF4(ElasticLF4):
         super(ExplicitElasticLF4, self).__init__(*args, **kwargs)
         self._dev = None
         self._halo = None
+        self._rec_local = None
         self.halo_mode = None
         self.steps_done = 0
         self.last_run_ms = None
@@ -160,7 +161,12 @@ class ExplicitElasticLF4(ElasticLF4):
                 raise capi.SgError("no CUDA device: seigen_b200 has no CPU fallback")
             plan = mesh_plan(self.mesh)
             device = torch.cuda.current_device()
-            self._dev = DeviceSolver(self.mesh, self.S.degree, device=device, plan=plan, symmetric=self._symmetric)
+            import os
+            # SG_GEOM_CLASSES=0: every cell keeps its own Jinv instead of sharing one record with its translates
+            # (sg_mesh_desc.geom_classes); the result is then independent of the partition bit for bit
+            classes = os.environ.get("SG_GEOM_CLASSES", "1") != "0"
+            self._dev = DeviceSolver(self.mesh, self.S.degree, device=device, plan=plan, symmetric=self._symmetric,
+                                     geom_classes=classes)
             if plan.nranks > 1:
                 import os
                 self.halo_mode = os.environ.get("SG_HALO", "peer")

@@ -72,12 +72,12 @@ def locate(coords, cells, point):
     return e, xi[e]
 
 
-def explosive_oracle(Lx, Ly, h, courant=0.05, degree=2, sigma_degree=4):
+def explosive_oracle(Lx, Ly, h, courant=0.05, degree=2, sigma_degree=4, nx=None, ny=None):
     """(oracle, source(t) callable, dt) for the explosive-source scenario on a Lx x Ly sub-domain (test infrastructure)."""
     from oracle.elastic_oracle import ElasticOracle
     from seigen_b200.mesh import RectangleMesh
-    mesh = RectangleMesh(int(Lx / h), int(Ly / h), Lx, Ly)
-    orc = ElasticOracle(mesh.coords, mesh.cells, degree, sigma_degree=sigma_degree)
+    mesh = RectangleMesh(nx or int(Lx / h), ny or int(Ly / h), Lx, Ly)
+    orc = ElasticOracle(mesh.coords, mesh.cells, degree, sigma_degree=sigma_degree, lite=True)
     orc.l, orc.mu, orc.density = EXPL_LAM, EXPL_MU, 1.0
     orc.dt = explosive_dt(h, courant)
     source, sponge = explosive_expressions(Lx, Ly)

@@ -112,3 +112,33 @@ def test_c_abi_exports_every_declared_symbol():
     assert capi.load().sg_version() >= 1
     assert capi.load().sg_nodes_per_cell(2, 2) == 6 and capi.load().sg_nodes_per_cell(3, 3) == 20
     assert capi.load().sg_nodes_per_cell(2, 7) < 0
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 3), (3, 2), (3, 3)])
+def test_vtu_output_carries_every_node(tmp_path, dim, p):
+    """File.write (seigen/elastic.py:120-124, 221-232): the snapshot holds all nd nodes of every cell, cut into p^d
+    linear sub-cells that tile the cell exactly; a .pvd collection indexes the series."""
+    from seigen_b200 import BoxMesh, File, Function, RectangleMesh, VectorFunctionSpace
+    from seigen_b200.vtkout import read_vtu_arrays, subcells
+    mesh = RectangleMesh(3, 2, 1.5, 1.0) if dim == 2 else BoxMesh(2, 1, 2, 1.0, 0.5, 1.0)
+    V = VectorFunctionSpace(mesh, "DG", p)
+    f = Function(V, name="VelocityNew")
+    rng = np.random.default_rng(0)
+    f.dat.data[...] = rng.standard_normal(f.dat.data.shape)
+    out = File(str(tmp_path / "velocity.pvd"))
+    out.write(f, time=0.25)
+    out.write(f, time=0.5)
+    a = read_vtu_arrays(tmp_path / "velocity_1.vtu")
+    E, nd = mesh.num_cells(), V.elem.nd
+    assert a["points"].shape == (E * nd, 3) and np.allclose(a["points"][:, :dim], V.node_coords())
+    assert np.array_equal(a["VelocityNew"][:, :dim], f.dat.data) and not a["VelocityNew"][:, dim:].any()
+    conn = a["connectivity"].reshape(-1, dim + 1)
+    assert len(conn) == E * p ** dim and set(a["types"]) == {5 if dim == 2 else 10}
+    # the sub-cells tile every cell: their volumes add up to the cell's
+    sub = subcells(V.elem)
+    x = V.elem.nodes[sub]                                         # (nsub, dim+1, dim) reference coordinates
+    vol = np.abs(np.linalg.det(x[:, 1:] - x[:, :1])).sum()
+    assert vol == pytest.approx(1.0)                               # |det| of the reference cell = 1 (x d!)
+    assert sorted(np.unique(sub)) == list(range(nd))               # every node is used
+    pvd = open(tmp_path / "velocity.pvd").read()
+    assert 'timestep="0.25"' in pvd and 'file="velocity_1.vtu"' in pvd

@@ -39,6 +39,26 @@ class EigenmodeLF4:
         uex, sex = eigenmode_expressions(self.dim, self.elastic.dt, 5, 5 + self.elastic.dt / 2.0)
         return errornorm_l2(u1, uex), errornorm_l2(s1, sex)
 
+    def error_as_reference(self, u1, s1):
+        """The reference's own functional (eigenmode_2d.py:40-65, eigenmode_3d.py:42-69): exact solution interpolated
+        into U / S, |difference| L2-projected into DG6 (2D) / DG3 (3D), norm of the projection."""
+        from seigen_b200 import (Function, TensorFunctionSpace, TestFunction, TrialFunction, VectorFunctionSpace, dx,
+                                 inner, lhs, norm, rhs, solve)
+        el = self.elastic
+        uex, sex = eigenmode_expressions(self.dim, el.dt, 5, 5 + el.dt / 2.0)
+        uexact = Function(el.U).interpolate(uex)
+        sexact = Function(el.S).interpolate(sex)
+        q = 6 if self.dim == 2 else 3
+        out = []
+        for space, f, exact in ((VectorFunctionSpace(self.mesh, "DG", q), u1, uexact),
+                                (TensorFunctionSpace(self.mesh, "DG", q), s1, sexact)):
+            temp = Function(space)
+            temp_test, temp_trial = TestFunction(space), TrialFunction(space)
+            G = inner(temp_test, temp_trial)*dx - inner(temp_test, abs(f - exact))*dx
+            solve(lhs(G) == rhs(G), temp)
+            out.append(norm(temp))
+        return tuple(out)
+
 
 MIN_RATES = {(2, 1): (1.5, 0.9), (2, 2): (2.8, 2.2), (2, 3): (3.7, 2.7), (3, 1): (0.8, 1.0), (3, 2): (3.0, 2.2)}
 
@@ -64,6 +84,11 @@ def test_eigenmode_errors_and_rates(dim, p, Ns):
             assert rel_err(s1.dat.data.reshape(s_o.shape), s_o[order]) < 1e-10
             # (the two error norms use different quadrature rules for the non-polynomial exact solution)
             assert eu == pytest.approx(eu_o, rel=2e-3) and es == pytest.approx(es_o, rel=2e-3)
+        if N <= 8:
+            # the reference's DG6 / DG3 projection norm measures || u1 - I_p u_exact || (interpolated exact solution):
+            # same order of magnitude as the true L2 error, never far above it
+            ru_, rs_ = em.error_as_reference(u1, s1)
+            assert 0.3 * eu < ru_ < 1.5 * eu and 0.3 * es < rs_ < 1.5 * es, (eu, ru_, es, rs_)
         errs.append((eu, es))
     if len(Ns) > 1:
         hs = [1.0 / N for N in Ns]
@@ -139,7 +164,25 @@ def test_run_twice_continues_and_output_mode(tmp_path, monkeypatch):
     assert n1 + b.elastic.steps_done == a.elastic.steps_done
     assert rel_err(ub.dat.data, ua) < 1e-12
     assert np.array_equal(b.elastic.u0.dat.data, ub.dat.data)
-    assert len(list(tmp_path.glob("velocity_*.vtk"))) == 2 * (n1 + 1)
+    assert len(list(tmp_path.glob("velocity_*.vtu"))) == 2 * (n1 + 1)
+    assert (tmp_path / "velocity.pvd").exists() and (tmp_path / "stress.pvd").exists()
+    # the last snapshot holds every node of the final field
+    from seigen_b200.vtkout import read_vtu_arrays
+    last = read_vtu_arrays(tmp_path / ("velocity_%d.vtu" % (2 * (n1 + 1) - 1)))
+    assert np.array_equal(last["VelocityNew"][:, :2], ub.dat.data)
+
+
+def test_output_every_k_steps(tmp_path, monkeypatch):
+    """``output_every = k``: snapshots after every k-th step and after the last one; the result does not change."""
+    monkeypatch.chdir(tmp_path)
+    a = EigenmodeLF4(2, 4, 1, eigenmode_dt(4, 1))
+    ua, _ = a.run(T=1.0)
+    b = EigenmodeLF4(2, 4, 1, eigenmode_dt(4, 1), output=True)
+    b.elastic.output_every = 3
+    ub, _ = b.run(T=1.0)
+    n = b.elastic.steps_done
+    assert n == a.elastic.steps_done and np.array_equal(ub.dat.data, ua.dat.data)
+    assert len(list(tmp_path.glob("velocity_*.vtu"))) == 1 + -(-n // 3)
 
 
 @pytest.mark.parametrize("p", [1, 2, 3])

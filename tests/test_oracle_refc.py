@@ -2,8 +2,11 @@
 tests/explosive_source/REF-C1 (fixture tests/golden/ref_c1.npz, made by scripts/make_golden.py), which
 tests/explosive_source/uy.py:36-43 overlays on -u_y at (45, 149).  The scenario of
 tests/explosive_source/explosive_source_lf4.py runs on a 100 x 50 m sub-domain below the same free surface with the
-stable time step.  REF-C1 comes from a different solver: the agreement is loose (waveform
-and amplitude to ~15 %), exactly what the reference itself only checks by eye."""
+stable time step.  REF-C1 comes from a different solver: measured agreement 12.6 % relative
+L2 over 0.1 <= t <= 0.45, peak ratio 1.047, peak 3.6 ms late -- the tolerances below are those numbers plus a
+margin; the reference itself only checks by eye.  The full 300 x 150 domain to T = 2.5 s (all three sensors) takes
+minutes on the CPU, so its traces are stored (tests/golden/oracle_refc_traces.npz, scripts/make_golden_traces.py)
+and compared with REF-C1..3 here; the GPU reproduces those traces in tests/test_gpu_fullsize.py."""
 import os
 
 import numpy as np
@@ -44,6 +47,26 @@ def test_oracle_tracks_ref_c1():
     times, trace = sensor_trace_oracle()
     rel, peak_ratio, dt_peak = compare_with_ref(times, trace)
     assert np.isfinite(trace).all() and np.abs(trace).max() < 1e-3          # stable (Courant 0.5 blows up, App. B-7)
-    assert rel < 0.25, rel
-    assert 0.8 < peak_ratio < 1.2, peak_ratio
-    assert abs(dt_peak) < 0.01, dt_peak
+    assert rel < 0.15, rel
+    assert 0.95 < peak_ratio < 1.15, peak_ratio
+    assert abs(dt_peak) < 0.006, dt_peak
+
+
+def test_stored_full_domain_traces_track_ref_c123():
+    """The oracle's traces on the shipped 120 x 60 mesh to T = 2.5 s, 0.3 m beside the sensors (interior points):
+    waveform correlation with REF-C1..3 >= 0.97 in the windows uy.py plots; amplitude 0.86 x at C1 (the near field
+    varies quickly beside the source; at the sensor itself it is 1.05 x, see test_oracle_tracks_ref_c1) and 2.2 x at
+    C2 / C3 (Rayleigh wave from a source 1 m deep on an h = 2.5 m mesh: not resolved -- documented, not hidden)."""
+    zt = np.load(os.path.join(os.path.dirname(GOLDEN), "oracle_refc_traces.npz"))
+    zr = np.load(os.path.join(os.path.dirname(GOLDEN), "ref_c123.npz"))
+    tt = zt["t"]
+    assert len(tt) == 2078
+    expected_amp = [(0.8, 0.95), (2.0, 2.45), (2.0, 2.45)]
+    for k, (lo, hi) in enumerate([(0.1, 1.0), (0.5, 1.5), (1.0, 2.5)]):
+        ref = np.interp(tt, zr["t"], zr["uy"][k])
+        w = (tt >= lo) & (tt <= hi)
+        sim = -zt["u"][w, k, 1]
+        corr = sim @ ref[w] / (np.linalg.norm(sim) * np.linalg.norm(ref[w]))
+        amp = (sim @ ref[w]) / (ref[w] @ ref[w])
+        assert corr > 0.97, (k, corr)
+        assert expected_amp[k][0] < amp < expected_amp[k][1], (k, amp)
