@@ -17,7 +17,14 @@ the reference makes -- K steps per call, host (page-locked) u0/s0 copied in and 
 region.  ``roofline`` is for the dominant kernel (pass K6, ``stage_g_kernel<AXPY>``); ``roofline_step`` for the
 whole step (64 B per DoF per step).  ``cpu_baseline`` / ``--impl reference`` time the C/OpenMP
 restatement of the reference's PyOP2 loop structure (``oracle/``; Firedrake itself cannot be installed here,
-DESIGN.md) on a bounded sample of the same workload on the host cores.
+DESIGN.md) on the host cores, all of them (OMP_NUM_THREADS=1 exported by torchrun is overridden): ``--impl reference``
+on the SAME 1532 x 484 P2 mesh, materials, source and dt as one GPU's share of this arm (53.4 M DoF, a few time
+steps); the ``cpu_baseline`` leg inside the GPU arm on the h = 24 m sample of it, to keep the default run short.
+
+``extra`` carries what the headline number does not show (``--extras none`` skips it): at N = 1 ``box3d``
+(BASELINE.json configs[4], UnitCubeMesh(26) P3) and ``elements`` (device-resident throughput of every supported
+element on a structured mesh); at N > 1 ``strong`` (the ONE 53.4 M-DoF model cut N ways: north_star's ">= 85 % at 8
+GPUs on a >= 50 M-DoF mesh") and ``box3d`` weak-scaled.
 """
 from __future__ import annotations
 
@@ -196,6 +203,49 @@ def sample_problem():
     return co, u, s, orc.dt, ndof, f"Marmousi 2D P{DEGREE} at h=24 m: {E} cells, {ndof} DoF"
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def full_problem_cpu(scale=1.0):
+    """The GPU arm's per-GPU workload for the CPU arm: same mesh (1532 x 484, h = 6 m), degree, per-cell Lame
+    parameters, Ricker source box, dt and kind of initial data as ``marmousi_problem(1)`` -- 53 387 136 DoF."""
+    from oracle.c_oracle import COracle
+    from oracle.elastic_oracle import ElasticOracle
+    from seigen_b200 import Expression
+    from seigen_b200.marmousi import marmousi_lame
+    from seigen_b200.mesh import RectangleMesh
+
+    nx, ny = max(2, int(round(NX * scale))), max(2, int(round(NY * scale)))
+    mesh = RectangleMesh(nx, ny, LX, LY)
+    orc = ElasticOracle(mesh.coords, mesh.cells, DEGREE, lite=True)
+    lam, mu = marmousi_lame(mesh)
+    orc.l, orc.mu, orc.density = lam, mu, 1.0
+    h = LX / nx
+    orc.dt = 0.5 * h / (2 ** (DEGREE - 1) * VP_MAX)
+    co = COracle(orc)
+    E, nd = orc.E, orc.nd
+    a = (np.pi * 10.0) ** 2
+    xc = LX * 0.5
+    box = RICKER.format(x0=xc - 0.5 * h, x1=xc + 0.5 * h, y0=LY - 1.5 * h, y1=LY - 0.5 * h)
+    expr = Expression(((box, "0.0"), ("0.0", box)), a=a, t0=0.1, t=0.0)
+    xs = orc.node_coords().reshape(-1, 2)
+    near = np.flatnonzero((np.abs(xs[:, 0] - xc) <= h) & (xs[:, 1] >= LY - 2 * h))
+    active = near[np.any(expr.evaluate(xs[near], t=0.1).reshape(len(near), -1) != 0, axis=1)]
+    src = np.zeros((E * nd, 2, 2))
+    src[active] = expr.evaluate(xs[active], t=orc.dt)
+    src = src.reshape(E, nd, 2, 2)
+    rng = np.random.default_rng(1234)
+    u = 1e-3 * rng.standard_normal((E, nd, 2))
+    s0 = 1e-3 * rng.standard_normal((E, nd, 2, 2))
+    s = np.ascontiguousarray(0.5 * (s0 + np.swapaxes(s0, 2, 3)))
+    ndof = E * nd * 6
+    return co, u, s, src, orc.dt, ndof, f"marmousi_2d_p{DEGREE}_{nx}x{ny}"
+
+
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
     --set full capture of this workload (profiles/dominant_kernel_traffic.json), or None if not captured yet."""
@@ -205,12 +255,12 @@ def profiled_traffic():
         return None
 
 
-def time_cpu(co, u, s, dt, steps, warmup):
+def time_cpu(co, u, s, dt, steps, warmup, src=None):
     for _ in range(warmup):
-        co.step_inplace(u, s, None, dt)
+        co.step_inplace(u, s, src, dt)
     t0 = time.perf_counter()
     for _ in range(steps):
-        co.step_inplace(u, s, None, dt)
+        co.step_inplace(u, s, src, dt)
     return time.perf_counter() - t0
 
 
@@ -219,23 +269,90 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    co, u, s, dt, ndof, sample = sample_problem()
-    # each bench step = one LF4 time step of the sample; cap so that the whole run stays within a few minutes
-    t_probe = time_cpu(co, u, s, dt, 1, 1)
-    steps = max(1, min(args.steps, int(120.0 / max(t_probe, 1e-6))))
-    warm = max(1, min(args.warmup, int(30.0 / max(t_probe, 1e-6))))
-    wall = time_cpu(co, u, s, dt, steps, warm)
+    t0 = time.perf_counter()
+    co, u, s, src, dt, ndof, wname = full_problem_cpu(args.scale)
+    cores = co.set_threads(host_threads())          # torchrun exports OMP_NUM_THREADS=1: use every core we may
+    setup = time.perf_counter() - t0
+    # each bench step = one LF4 time step of the full per-GPU mesh (~1 s on 16+ cores); capped so that the whole run
+    # stays within a few minutes
+    t_probe = time_cpu(co, u, s, dt, 1, 0, src)
+    steps = max(1, min(args.steps, int(60.0 / max(t_probe, 1e-6))))
+    warm = max(0, min(args.warmup, int(15.0 / max(t_probe, 1e-6))))
+    wall = time_cpu(co, u, s, dt, steps, warm, src)
     val = ndof * steps / wall
+    world = env_int("WORLD_SIZE", 1)
+    sample = (f"{wname}: the GPU arm's mesh, degree, per-cell materials, Ricker source and dt for ONE GPU "
+              f"({ndof} DoF), {steps} time steps" + ("" if world == 1 else f" -- 1/{world} of the {world}-GPU workload"))
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"marmousi_2d_p{DEGREE}", "sample": sample, "degree": DEGREE,
+           "config": {"workload": wname + "_per_gpu", "degree": DEGREE, "dim": 2, "dof": int(ndof), "dt": dt,
+                      "sample": sample, "setup_s": setup,
+                      "material": "per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1",
                       "note": "Firedrake/PyOP2 cannot be installed here; this is the C/OpenMP restatement of the "
-                              "reference's PyOP2 loop structure (oracle/elastic_c.c), all host threads"},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": co.threads, "kind": "port", "sample": sample},
+                              "reference's PyOP2 loop structure (oracle/elastic_c.c: 25 sweeps per step), all host "
+                              "threads"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+ELEMENT_MESHES = [   # (dim, degree, builder arguments): structured meshes of ~25-55 M DoF, as scripts/perf_probe.py
+    (2, 1, (1532, 484)), (2, 2, (1532, 484)), (2, 3, (1000, 400)), (2, 4, (800, 300)),
+    (3, 1, (128, 32, 32)), (3, 2, (64, 32, 32)), (3, 3, (64, 32, 16)),
+]
+
+
+def element_table(steps, peak):
+    """Device-resident DoF-updates/s of every supported element (constant material, no source, symmetric stress
+    storage), C ABI driven directly: the kernels behind BASELINE.json configs[0]-[4] beside the headline one."""
+    from seigen_b200.device import DeviceSolver
+    from seigen_b200.mesh import BoxMesh, RectangleMesh
+    from seigen_b200.refelem import get_refelem
+    rows = []
+    for d, p, n in ELEMENT_MESHES:
+        mesh = RectangleMesh(n[0], n[1], LX, LY) if d == 2 else BoxMesh(n[0], n[1], n[2], 4.0, 1.0, 1.0)
+        nd = get_refelem(d, p).nd
+        E = mesh.num_cells()
+        ndof = E * nd * (d + d * d)
+        dev = DeviceSolver(mesh, p, symmetric=True)
+        dev.set_material(1.0, 0.5, 0.25)
+        rng = np.random.default_rng(0)
+        u = 1e-3 * rng.standard_normal((E * nd, d))
+        s = 1e-3 * rng.standard_normal((E * nd, d, d))
+        dev.set_state(u, 0.5 * (s + np.swapaxes(s, 1, 2)))
+        dev.step(3, 1e-6)
+        dev.synchronize()
+        best = None
+        for _ in range(2):
+            dev.step(steps, 1e-6)
+            ms = dev.last_step_ms() / steps
+            best = ms if best is None else min(best, ms)
+        dev.close()
+        rows.append({"dim": d, "degree": p, "cells": int(E), "dof": int(ndof), "ms_per_step": best,
+                     "value": ndof / (best * 1e-3), "roofline_step_frac": 64.0 * ndof / (best * 1e-3) / 1e9 / peak})
+    return rows
+
+
+def device_value(el, K, W, barrier, max_over_ranks, sum_over_ranks):
+    """K steps after W warm-up steps, state resident in HBM, CUDA events on the solver's stream, max over ranks."""
+    dt = float(el.dt)
+    el.run((W + 0.5) * dt)                      # plan, upload of geometry / material / source table, graph (untimed)
+    dev = el._dev
+    nd, d = el.S.elem.nd, el.dimension
+    ndof_local = dev.n_owned * nd * (d + d * d)
+    ndof = sum_over_ranks(ndof_local)
+    el.setup([dt * (i + 1) for i in range(K)])
+    el._upload_state()
+    el._advance(W, 0)
+    barrier()
+    el._advance(K, 0)
+    barrier()
+    ms = max_over_ranks(dev.last_step_ms())
+    el._check_peers("bench")
+    return {"value": ndof * K / (ms * 1e-3), "ms_per_step": ms / K, "dof_total": int(ndof),
+            "dof_per_gpu": int(ndof_local), "cells_per_gpu": int(dev.n_owned), "steps": K}
 
 
 def run_gpu(args):
@@ -307,10 +424,10 @@ def run_gpu(args):
     ms = max_over_ranks(ms_local)
     value = ndof * K / (ms * 1e-3)
     step_counter = 1 if el.source_function is not None else 0     # the source is added inside the G-type passes
-    if world == 1:
-        launches = K * (6 + step_counter)                         # six fused passes (+ device-side step counter)
-    else:                                                         # per pass: boundary, interior, push, signal, wait
-        launches = K * (6 * 5 + step_counter)
+    if world == 1 or not os.environ.get("SG_PEER_SCHED_SPLIT"):
+        launches = K * (6 + step_counter)       # six fused passes (+ device-side step counter); with peers the halo
+    else:                                       # exchange rides inside the same six kernels
+        launches = K * (6 * 5 + step_counter)   # two-stream schedule: boundary, interior, push, signal, wait per pass
 
     # ---- per-pass timing of the six kernels (roofline of the dominant one) ----------------------------------
     reps = max(10, min(K, 50))
@@ -382,32 +499,66 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu and args.workload == "marmousi":
         co, u, s, cdt, cndof, sample = sample_problem()
+        co.set_threads(host_threads())
         t1 = time_cpu(co, u, s, cdt, 1, 1)
         csteps = max(2, min(60, int(15.0 / max(t1, 1e-6))))
         cw = time_cpu(co, u, s, cdt, csteps, 0)
         cpu = {"value": cndof * csteps / cw, "unit": UNIT, "cores": co.threads, "kind": "port",
                "sample": f"{sample}, {csteps} steps"}
 
+    degree, halo_mode, symmetric = int(el.S.degree), el.halo_mode, bool(dev.symmetric)
+    # ---- extras: what the headline does not show (3D, strong scaling, the other elements) -------------------------
+    extra = {}
+    if args.extras != "none":
+        el.close()
+        del el
+        import gc
+        gc.collect()
+        Kx = max(10, min(K, 50))
+        if args.workload == "marmousi":
+            b3, b3name = box3d_problem(world)
+            r = device_value(b3, Kx, W, barrier, max_over_ranks, sum_over_ranks)
+            r.update(workload=b3name, scaling="weak", n_gpus=world,
+                     roofline_step_frac=64.0 * r["dof_per_gpu"] / (r["ms_per_step"] * 1e-3) / 1e9 / peak,
+                     note="BASELINE.json configs[4]: UnitCubeMesh(N) P3, N = 26/33/41/52 for 1/2/4/8 GPUs")
+            extra["box3d"] = r
+            b3.close()
+            del b3
+            gc.collect()
+        if world > 1 and args.workload == "marmousi" and not strong:
+            st, stname = marmousi_problem(world, args.scale, strong=True)
+            r = device_value(st, Kx, W, barrier, max_over_ranks, sum_over_ranks)
+            r.update(workload=stname, scaling="strong", n_gpus=world,
+                     note="the ONE 53.4 M-DoF Marmousi model cut into n_gpus parts (north_star: >= 85 percent at 8 GPUs); "
+                          "efficiency = value / (n_gpus * value of the N = 1 run); the per-GPU state is "
+                          f"{8e-6 * r['dof_per_gpu']:.0f} MB (the L2 holds 126 MB)")
+            extra["strong"] = r
+            st.close()
+            del st
+            gc.collect()
+        if world == 1:
+            extra["elements"] = element_table(20, peak)
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
-               "config": {"workload": wname, "degree": int(el.S.degree), "dim": int(d), "cells_per_gpu": int(E),
+               "config": {"workload": wname, "degree": degree, "dim": int(d), "cells_per_gpu": int(E),
                           "dof_per_gpu": int(ndof_local), "dof_total": int(ndof), "dt": dt,
                           "material": ("per-cell lambda=mu=Vp^2/3 from the Marmousi grid, rho=1"
                                        if args.workload == "marmousi" else "constant lambda=0.5, mu=0.25, rho=1"),
                           "source": "Ricker, one cell box per tile" if args.workload == "marmousi" else "none",
                           "sponge": "none",
                           "initial_data": "random 1e-3 velocity, random 1e-3 symmetric stress",
-                          "stress_storage": "symmetric (upper triangle)" if dev.symmetric else "full",
+                          "stress_storage": "symmetric (upper triangle)" if symmetric else "full",
                           "l2": ("state 8*dof_per_gpu bytes = %.0f MB > 126 MB L2 (no flush needed)"
                                  if 8 * ndof_local > 126e6 else
                                  "state 8*dof_per_gpu bytes = %.0f MB fits the 126 MB L2: not an HBM measurement "
                                  "(strong-scaling / reduced-scale run)") % (8e-6 * ndof_local),
-                          "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass, exchange={el.halo_mode}",
+                          "parallelism": f"mesh partition rcb x{world}, one-layer DG halo per pass, exchange={halo_mode}",
                           "setup_s": t_setup},
                "roofline": roofline, "roofline_step": roofline_step, "stages": stages,
-               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extra": extra}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -424,6 +575,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="marmousi", choices=["marmousi", "box3d"],
                     help="marmousi (default, the headline: BASELINE.json configs[3]); box3d: configs[4], 3D P3 weak scaling")
+    ap.add_argument("--extras", default="auto", choices=["auto", "none"],
+                    help="auto (default): add the `extra` records (box3d, strong scaling at N > 1, element table at N = 1)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's scaling run): 53.4 M DoF per GPU; strong: 53.4 M DoF in total")
     args = ap.parse_args()

@@ -45,6 +45,8 @@ def _load():
         build()
         _lib = C.CDLL(LIB)
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_set_threads.argtypes = [C.c_int]
+        _lib.oracle_set_threads.restype = None
         _lib.oracle_solve_f.argtypes = [C.POINTER(_Ctx), _P, _P, _P, _P]
         _lib.oracle_solve_g.argtypes = [C.POINTER(_Ctx), _P, _P, _P, _P]
         _lib.oracle_step.argtypes = [C.POINTER(_Ctx), _P, _P, _P, C.c_double] + [_P] * 6
@@ -81,18 +83,28 @@ class COracle:
                 phif[f, pi] = orc.el.tab(x)
         cells = orc.cells
 
-        def perm_of(e, f, ref_gids):
-            """order in which cell e's facet-f vertices must be taken to follow the global ids ref_gids."""
-            loc = [vid[f].index(int(np.flatnonzero(cells[e] == g)[0])) for g in ref_gids]
-            return pidx[tuple(loc)]
-
+        # perm-: the order in which the '-' cell's facet vertices must be taken to follow the '+' cell's facet vertices
+        # (matched through their global ids), as an index into `perms`
+        ident = pidx[tuple(range(d))]
+        vid_a = np.array(vid)                                                   # (d+1, d) local vertices of facet f
         ifac = np.zeros((len(orc.int_facets), 6), dtype=np.int32)
-        for n, (ep, fp, em, fm) in enumerate(orc.int_facets):
-            gids = cells[ep][vid[fp]]
-            ifac[n] = (ep, fp, pidx[tuple(range(d))], em, fm, perm_of(em, fm, gids))
+        if len(ifac):
+            ep, fp, em, fm = orc.int_facets.T
+            gp = cells[ep[:, None], vid_a[fp]]                                  # (n, d) global ids, '+' side order
+            gm = cells[em[:, None], vid_a[fm]]                                  # (n, d) global ids, '-' side order
+            loc = np.argmax(gm[:, None, :] == gp[:, :, None], axis=2)           # loc[n, j]: where gp[n, j] sits in gm[n]
+            assert np.all(np.take_along_axis(gm, loc, axis=1) == gp)
+            code = (loc * (d ** np.arange(d))[None, :]).sum(axis=1)
+            lut = np.full(d ** d, -1, dtype=np.int32)
+            for perm, i in pidx.items():
+                lut[sum(perm[j] * d ** j for j in range(d))] = i
+            pm = lut[code]
+            assert (pm >= 0).all()
+            ifac[:, 0], ifac[:, 1], ifac[:, 2] = ep, fp, ident
+            ifac[:, 3], ifac[:, 4], ifac[:, 5] = em, fm, pm
         efac = np.zeros((len(orc.ext_facets), 3), dtype=np.int32)
-        for n, (e, f) in enumerate(orc.ext_facets):
-            efac[n] = (e, f, pidx[tuple(range(d))])
+        if len(efac):
+            efac[:, 0], efac[:, 1], efac[:, 2] = orc.ext_facets[:, 0], orc.ext_facets[:, 1], ident
         if orc.iF is not None:
             inrm = np.ascontiguousarray(orc.iF["n_plus"])
             imeas = np.ascontiguousarray(orc.iF["w"][:, 0] / orc.fw_ref[0])
@@ -120,6 +132,11 @@ class COracle:
     @property
     def threads(self):
         return int(self.lib.oracle_num_threads())
+
+    def set_threads(self, n):
+        """Use ``n`` OpenMP threads from now on, whatever OMP_NUM_THREADS said at start-up."""
+        self.lib.oracle_set_threads(int(n))
+        return self.threads
 
     def sync_parameters(self):
         orc = self.orc

@@ -66,6 +66,16 @@ static int nthreads_(void) {
 
 int oracle_num_threads(void) { return nthreads_(); }
 
+/* Overrides OMP_NUM_THREADS for this process (torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is
+ * meant to use all the host cores it can, bench.py). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static void chunk(int64_t n, int t, int nt, int64_t* lo, int64_t* hi) {
   *lo = n * t / nt;
   *hi = n * (t + 1) / nt;

@@ -231,18 +231,37 @@ class ElasticOracle:
     def _build_facets(self):
         d, E = self.dim, self.E
         cells, coords = self.cells, self.coords
-        seen = {}
-        interior, exterior = [], []
-        for e in range(E):
-            for f in range(d + 1):
-                key = tuple(sorted(int(x) for i, x in enumerate(cells[e]) if i != f))
-                if key in seen:
-                    interior.append(seen.pop(key) + (e, f))
-                else:
-                    seen[key] = (e, f)
-        exterior = sorted(seen.values())
-        self.int_facets = np.array(interior, dtype=np.int64).reshape(-1, 4)     # e+, f+, e-, f-
-        self.ext_facets = np.array(exterior, dtype=np.int64).reshape(-1, 2)
+        # facet matching through the sorted vertex tuple of every (cell, facet).  Small meshes: a dictionary, visited
+        # in (cell, facet) order; large meshes: the same pairs in the same order from one sort (an interior facet is
+        # listed where its SECOND cell meets it, as the dictionary walk does).
+        if E <= 20000:
+            seen = {}
+            interior, exterior = [], []
+            for e in range(E):
+                for f in range(d + 1):
+                    key = tuple(sorted(int(x) for i, x in enumerate(cells[e]) if i != f))
+                    if key in seen:
+                        interior.append(seen.pop(key) + (e, f))
+                    else:
+                        seen[key] = (e, f)
+            exterior = sorted(seen.values())
+            self.int_facets = np.array(interior, dtype=np.int64).reshape(-1, 4)     # e+, f+, e-, f-
+            self.ext_facets = np.array(exterior, dtype=np.int64).reshape(-1, 2)
+        else:
+            nf = d + 1
+            keys = np.stack([np.sort(np.delete(cells, f, axis=1), axis=1) for f in range(nf)], axis=1).reshape(E * nf, d)
+            order = np.lexsort(keys.T[::-1])                  # groups equal tuples; stable: visit order inside a group
+            ks = keys[order]
+            same = np.all(ks[1:] == ks[:-1], axis=1)
+            first, second = order[:-1][same], order[1:][same]
+            by_second = np.argsort(second, kind="stable")
+            first, second = first[by_second], second[by_second]
+            self.int_facets = np.stack([first // nf, first % nf, second // nf, second % nf], axis=1).astype(np.int64)
+            paired = np.zeros(E * nf, dtype=bool)
+            paired[first] = True
+            paired[second] = True
+            ext = np.flatnonzero(~paired)
+            self.ext_facets = np.stack([ext // nf, ext % nf], axis=1).astype(np.int64)
 
         fq, fw = simplex_quadrature(d - 1, 2 * self.p) if d > 1 else (np.zeros((1, 0)), np.ones(1))
         self.fw_ref = fw

@@ -1,0 +1,72 @@
+"""Per-pass timing of every compiled kernel variant of one element (development aid; C ABI driven directly).
+
+    python scripts/tune_stages.py --dim 3 --degree 3 --nx 64 --ny 32 --nz 16
+
+For each variant in the library's table that matches (dim, degree) -- selected through SG_TILE / SG_SPLIT / SG_MINB /
+SG_MINBA / SG_NS, which sg_create reads -- prints ms of the six passes (sg_time_stage) and of a whole step (sg_step).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from seigen_b200.device import DeviceSolver  # noqa: E402
+from seigen_b200.mesh import BoxMesh, RectangleMesh  # noqa: E402
+from seigen_b200.refelem import get_refelem  # noqa: E402
+
+VARIANTS = {   # (tile, split, minb, minba, ns) as compiled in csrc/sg_inst_*.cu
+    (2, 1): [(128, 1, 4, 2, 22), (64, 1, 8, 4, 22)],
+    (2, 2): [(64, 1, 8, 3, 22), (64, 1, 10, 3, 22), (128, 1, 4, 2, 22), (64, 2, 4, 3, 22), (128, 1, 4, 2, 32),
+             (64, 1, 8, 3, 32), (32, 1, 16, 6, 22), (32, 1, 16, 6, 32)],
+    (2, 3): [(32, 1, 8, 4, 22), (64, 1, 4, 2, 22)],
+    (2, 4): [(32, 1, 4, 3, 22)],
+    (3, 1): [(64, 1, 4, 3, 22), (64, 1, 6, 3, 22), (32, 1, 8, 4, 22), (32, 3, 4, 4, 32), (64, 1, 4, 3, 32),
+             (32, 1, 8, 4, 32), (32, 1, 12, 6, 22)],
+    (3, 2): [(32, 3, 3, 3, 22), (32, 3, 4, 4, 22), (32, 3, 3, 3, 32), (64, 3, 2, 2, 22), (32, 1, 4, 4, 22),
+             (32, 3, 5, 4, 22)],
+    (3, 3): [(32, 3, 2, 2, 22), (32, 3, 2, 2, 21), (32, 3, 3, 3, 22), (32, 3, 3, 3, 11), (32, 3, 2, 2, 11),
+             (32, 3, 3, 2, 12)],
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dim", type=int, default=2)
+    ap.add_argument("--degree", type=int, default=2)
+    ap.add_argument("--nx", type=int, default=1532)
+    ap.add_argument("--ny", type=int, default=484)
+    ap.add_argument("--nz", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--tag", default="")
+    a = ap.parse_args()
+    mesh = RectangleMesh(a.nx, a.ny, 9192.0, 2904.0) if a.dim == 2 else BoxMesh(a.nx, a.ny, a.nz, 4.0, 1.0, 1.0)
+    el = get_refelem(a.dim, a.degree)
+    E, d = mesh.num_cells(), a.dim
+    ndof = E * el.nd * (d + d * d)
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal((E * el.nd, d)) * 1e-3
+    s = rng.standard_normal((E * el.nd, d, d)) * 1e-3
+    s = 0.5 * (s + np.swapaxes(s, 1, 2))
+    for tile, split, minb, minba, ns in VARIANTS[(a.dim, a.degree)]:
+        os.environ.update(SG_TILE=str(tile), SG_SPLIT=str(split), SG_MINB=str(minb), SG_MINBA=str(minba), SG_NS=str(ns))
+        dev = DeviceSolver(mesh, a.degree, symmetric=True)
+        dev.set_material(1.0, 0.5, 0.25)
+        dev.set_state(u, s)
+        dt = 1e-6
+        dev.step(3, dt)
+        dev.synchronize()
+        st = [dev.time_stage(k, dt, 10) for k in range(1, 7)]
+        best = 1e9
+        for _ in range(2):
+            dev.step(a.steps, dt)
+            best = min(best, dev.last_step_ms() / a.steps)
+        print(f"{a.tag} d{d}p{a.degree} tile={tile} split={split} minb={minb}/{minba} ns={ns}: "
+              + " ".join(f"K{k + 1}={1e3 * t:.1f}" for k, t in enumerate(st))
+              + f" | step {best:.4f} ms {ndof / best / 1e6:.2f} Gupd/s", flush=True)
+        dev.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,12 +49,13 @@ int env_int(const char* name) {
 
 const Variant* find_variant(int dim, int degree) {
   const int tile = env_int("SG_TILE"), split = env_int("SG_SPLIT"), minb = env_int("SG_MINB"), ns = env_int("SG_NS");
+  const int minba = env_int("SG_MINBA");
   const Variant* first = nullptr;
   for (const Variant& v : variants()) {
     if (v.dim != dim || v.degree != degree) continue;
     if (!first) first = &v;
     if ((tile == 0 || v.tile == tile) && (split == 0 || v.split == split) && (minb == 0 || v.minb == minb) &&
-        (ns == 0 || v.ns_plain * 10 + v.ns_axpy == ns))
+        (minba == 0 || v.minba == minba) && (ns == 0 || v.ns_plain * 10 + v.ns_axpy == ns))
       return &v;
   }
   return first;
@@ -164,7 +165,10 @@ sg::StageParams base_params(sg_solver* h) {
 int field_ncomp(sg_solver* h, int which);
 const int STAGE_OUTPUT[7] = {-1, SG_FIELD_UH, SG_FIELD_SH, SG_FIELD_U, SG_FIELD_SH, SG_FIELD_UH, SG_FIELD_S};
 
-int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, bool push = false) {
+// in_step: the launch is one of the six of a captured time step (chained with programmatic dependent launch; the
+// last one advances the step counter)
+int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, bool push = false,
+                 bool in_step = false) {
   int t0 = 0, nt = h->tiles_owned;
   if (part == SG_PART_BOUNDARY) {
     nt = h->tiles_boundary;
@@ -224,6 +228,9 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
     p.nsteps = h->src_steps;
     p.nsrc = h->nsrc;
   }
+  // the device-side step counter (source table index, receivers) advances with the last pass of a step; with
+  // receivers a separate kernel does it after they have been sampled
+  if (in_step && stage == 6 && h->nsrc > 0 && h->nrec == 0) p.bump = h->step_dev.p;
   if (push && h->npeers > 0 && h->push_tiles > 0) {
     // halo exchange of this pass's output fused into the kernel (sg::halo_wait / sg::halo_push)
     const int which = STAGE_OUTPUT[stage];
@@ -262,7 +269,21 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
     }
     if (grid > nt) grid = nt;
     void* args[] = {(void*)&p};
-    if (part == SG_PART_BOUNDARY && env_int("SG_LAUNCH_PRIORITY") > 0) {
+    if (in_step && env_int("SG_NO_PDL") == 0) {
+      // programmatic dependent launch: this kernel's launch + CTA prologue overlap the previous pass's tail
+      // (sg::pdl_wait in the kernel orders every read of the previous output)
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr.val.programmaticStreamSerializationAllowed = 1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(nthreads);
+      cfg.dynamicSmemBytes = pl.total;
+      cfg.stream = st;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      SG_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    } else if (part == SG_PART_BOUNDARY && env_int("SG_LAUNCH_PRIORITY") > 0) {
       // experiment for the next round (off by default, unmeasured): give the boundary kernel node an explicit
       // priority inside the captured graph instead of relying on the comm stream's
       int least = 0, greatest = 0;
@@ -358,7 +379,7 @@ int enqueue_step_peers(sg_solver* h, double dt) {
 // nothing on the critical path unless a peer is late.
 int enqueue_step_fused(sg_solver* h, double dt) {
   for (int k = 1; k <= 6; ++k) {
-    int rc = launch_stage(h, k, SG_PART_ALL, dt, h->stream, true);
+    int rc = launch_stage(h, k, SG_PART_ALL, dt, h->stream, true, true);
     if (rc) return rc;
   }
   return SG_OK;
@@ -858,11 +879,12 @@ int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
     else if (h->npeers > 0)
       rc = enqueue_step_fused(h, dt);
     else
-      for (int k = 1; k <= 6 && rc == SG_OK; ++k) rc = launch_stage(h, k, SG_PART_ALL, dt, st);
+      for (int k = 1; k <= 6 && rc == SG_OK; ++k) rc = launch_stage(h, k, SG_PART_ALL, dt, st, false, true);
     if (rc == SG_OK && h->nrec > 0)
       sg::receivers_kernel<<<1, 128, 0, st>>>(h->u.p, h->rec_cell.p, h->rec_w.p, h->rec_data.p, h->step_dev.p,
                                               h->rec_steps, (int)h->nrec, h->nd, h->dim, h->tile);
-    if (rc == SG_OK && (h->nsrc > 0 || h->nrec > 0)) sg::bump_step_kernel<<<1, 1, 0, st>>>(h->step_dev.p);
+    const bool split_sched = h->npeers > 0 && env_int("SG_PEER_SCHED_SPLIT") > 0;
+    if (rc == SG_OK && (h->nrec > 0 || (h->nsrc > 0 && split_sched))) sg::bump_step_kernel<<<1, 1, 0, st>>>(h->step_dev.p);
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc != SG_OK) {
       if (g) cudaGraphDestroy(g);
@@ -1061,6 +1083,9 @@ int sg_peer_connect(sg_solver* h, int32_t npeers, const sg_peer_desc* peers) {
   SG_CUDA(cudaStreamSynchronize(h->comm));
   h->config_version++;
   h->npeers = 0;
+  drop_graph(h);                                   // the step graph holds the peers' pointers
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->ipc_opened.clear();
   if (npeers == 0) return SG_OK;
   std::vector<double*> rf((size_t)4 * npeers);
   std::vector<unsigned long long*> fl((size_t)npeers);

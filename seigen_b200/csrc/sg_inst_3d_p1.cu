@@ -9,4 +9,7 @@ void sg_variants_3d_p1(std::vector<Variant>& v) {
   v.push_back(make_variant<3, 1, 64, 1, 6, 3, 2, 2, true, false>());
   v.push_back(make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>());
   v.push_back(make_variant<3, 1, 32, 3, 4, 4, 3, 2, true, false>());
+  v.push_back(make_variant<3, 1, 64, 1, 4, 3, 3, 2, true, false>());
+  v.push_back(make_variant<3, 1, 32, 1, 8, 4, 3, 2, true, true>());
+  v.push_back(make_variant<3, 1, 32, 1, 12, 6, 2, 2, true, true>());
 }

@@ -7,4 +7,8 @@
 void sg_variants_3d_p2(std::vector<Variant>& v) {
   v.push_back(make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>());
   v.push_back(make_variant<3, 2, 32, 3, 4, 4, 2, 2, true, false>());
+  v.push_back(make_variant<3, 2, 32, 3, 3, 3, 3, 2, true, false>());
+  v.push_back(make_variant<3, 2, 64, 3, 2, 2, 2, 2, true, false>());
+  v.push_back(make_variant<3, 2, 32, 1, 4, 4, 2, 2, true, false>());
+  v.push_back(make_variant<3, 2, 32, 3, 5, 4, 2, 2, true, false>());
 }

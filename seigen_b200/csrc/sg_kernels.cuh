@@ -72,6 +72,8 @@ struct StageParams {
   unsigned long long* ctl;              // my control words (SG_CTL_*)
   unsigned long long* const* rflag;     // [npeers] my flag slot in each peer's control words
   long long timeout_cycles;
+  int64_t* bump;                        // last pass of a step inside the step graph: the CTA that finishes last
+                                        // advances the device-side step counter (nullptr otherwise)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -331,15 +333,23 @@ __device__ __forceinline__ void issue_tile(const StageParams& p, const StagePlan
   if (pl.abs_b) bulk_g2s(stage + pl.abs, p.absidx + (size_t)tile * (pl.abs_b / 4), pl.abs_b, bar);
 }
 
+// Programmatic dependent launch (sm_90+): the stage kernels of a step are chained with programmatic edges, so the
+// launch and the CTA prologue of pass k+1 (barrier init, table copies) overlap the tail of pass k.  pdl_launch lets the
+// next kernel in the stream start being scheduled once every CTA of this grid has started; pdl_wait blocks until the
+// previous kernel has completed and its writes are visible (a no-op for a kernel launched without the attribute).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Dynamic tile scheduler.  CTA b starts with tile b; further tiles are tickets gridDim.x + atomicAdd(next).  A
 // ticket is requested one iteration before its bulk copies are issued, so the atomic's latency is never waited
 // for.  The last CTA to finish zeroes both words for the next launch on the stream.
 __device__ __forceinline__ int sched_next(unsigned int* sched) { return (int)(gridDim.x + atomicAdd(sched, 1u)); }
-__device__ __forceinline__ void sched_done(unsigned int* sched) {
+__device__ __forceinline__ void sched_done(unsigned int* sched, int64_t* bump = nullptr) {
   __threadfence();
   if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
     sched[0] = 0u;
     sched[1] = 0u;
+    if (bump != nullptr) *bump += 1;
     __threadfence();
   }
 }
@@ -501,7 +511,9 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
   const unsigned char* sft = smem + pl.ftab;
   const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
+  pdl_launch_dependents();
   cta_setup<NS, NT>(p, pl, smem, E::ftab(), E::FTAB_SIZE, D * D);
+  pdl_wait();   // everything above reads tables that no kernel writes; from here on the previous pass's output is read
 
   const int tid = threadIdx.x, lane = tid % TILE, ig = tid / TILE;
   SG_PIPE_PROLOGUE(false)
@@ -604,7 +616,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     __syncthreads();   // the stage may be refilled from the next iteration on
     if (btile) halo_push<TILE, NT>(p, tile);
   }
-  if (tid == 0) sched_done(p.sched);
+  if (tid == 0) sched_done(p.sched, p.bump);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -624,7 +636,9 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
   const unsigned char* sft = smem + pl.ftab;
   const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
   double* sX = reinterpret_cast<double*>(smem + pl.x);
+  pdl_launch_dependents();
   cta_setup<NS, NT>(p, pl, smem, E::ftab(), E::FTAB_SIZE, D * D);
+  pdl_wait();   // (see stage_f_kernel)
 
   const int tid = threadIdx.x, lane = tid % TILE, ig = tid / TILE;
   SG_PIPE_PROLOGUE(true)
@@ -748,7 +762,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
       halo_push<TILE, NT>(p, tile);
     }
   }
-  if (tid == 0) sched_done(p.sched);
+  if (tid == 0) sched_done(p.sched, p.bump);
 }
 
 #ifndef SG_STAGE_KERNELS_ONLY   // the instantiation units (sg_inst_*.cu) only need the stage kernels

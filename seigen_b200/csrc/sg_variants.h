@@ -7,7 +7,7 @@
 #include "sg_kernels.cuh"
 
 struct Variant {
-  int dim, degree, nd, nfp, tile, split, minb, ns_plain, ns_axpy, axs;
+  int dim, degree, nd, nfp, tile, split, minb, minba, ns_plain, ns_axpy, axs;
   // [0]: full stress storage (D*D components), [1]: symmetric storage (upper triangle)
   sg::StagePlan (*plan_f[2])(bool classes, bool mat, bool sponge);
   sg::StagePlan (*plan_f_axpy[2])(bool classes, bool mat, bool sponge);
@@ -47,6 +47,7 @@ inline Variant make_variant() {
   v.tile = TILE;
   v.split = SPLIT;
   v.minb = MINB;
+  v.minba = MINBA;
   v.ns_plain = NSP;
   v.ns_axpy = NSA;
   v.axs = AXS;

@@ -197,14 +197,29 @@ class ExplicitElasticLF4(ElasticLF4):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return bool(t.item() > 0)
 
-    def _fall_back_to_full_storage(self):
-        log("stress or source not symmetric: switching to full stress storage")
-        self._symmetric = False
-        if self._dev is not None:
-            self._dev.close()
+    def close(self):
+        """Release the device solver.  With peers: every rank first unmaps its neighbours' buffers, then all ranks
+        meet, and only then is device memory freed -- no rank frees a buffer another one still has mapped.
+        Collective when the mesh is partitioned."""
+        dev = self._dev
+        if dev is None:
+            return
+        if dev.plan.nranks > 1:
+            if self.halo_mode == "peer":
+                dev.synchronize()
+                check(lib.sg_peer_connect(dev.handle, 0, None))
+            import torch.distributed as dist
+            dist.barrier()
+        dev.close()
         self._dev = None
         self._halo = None
         self._source_key = None
+        self._material_on_device = None
+
+    def _fall_back_to_full_storage(self):
+        log("stress or source not symmetric: switching to full stress storage")
+        self._symmetric = False
+        self.close()
 
     def setup(self, times=None):
         """Upload parameters (the role of elastic.py:244-255 + 369-385: nothing is assembled or inverted here,

@@ -79,17 +79,29 @@ def hilbert_order(centroids: np.ndarray) -> np.ndarray:
     return np.argsort(hilbert_key(centroids), kind="stable")
 
 
-def _rcb(centroids, ids, nparts, out, first):
+def _rcb(cols, ids, nparts, out, first):
+    """Recursive coordinate bisection on ``cols`` = one contiguous coordinate array per axis, restricted to ``ids``
+    (ascending).  The split position is found with a selection (O(n)), not a sort; cells whose coordinate ties with
+    the split value go left in index order, which is what a stable sort would do (structured meshes have thousands
+    of equal centroid coordinates: the cut stays a clean plane)."""
     if nparts == 1:
         out[ids] = first
         return
     left_parts = nparts // 2
-    c = centroids[ids]
-    axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
-    k = int(round(len(ids) * left_parts / nparts))
-    order = np.argsort(c[:, axis], kind="stable")
-    _rcb(centroids, ids[order[:k]], left_parts, out, first)
-    _rcb(centroids, ids[order[k:]], nparts - left_parts, out, first + left_parts)
+    sub = [c[ids] if ids is not None else c for c in cols]
+    axis = int(np.argmax([float(x.max() - x.min()) for x in sub]))
+    x = sub[axis]
+    n = len(x)
+    k = int(round(n * left_parts / nparts))
+    if k <= 0 or k >= n:
+        raise ValueError("more parts than cells")
+    v = np.partition(x, k - 1)[k - 1]                 # k-th smallest coordinate
+    left = x < v
+    ties = np.flatnonzero(x == v)
+    left[ties[:k - int(np.count_nonzero(left))]] = True
+    idx = np.arange(n) if ids is None else ids
+    _rcb(cols, idx[left], left_parts, out, first)
+    _rcb(cols, idx[~left], nparts - left_parts, out, first + left_parts)
 
 
 def partition_cells(mesh: Mesh, nparts: int, method: str = "rcb") -> np.ndarray:
@@ -99,7 +111,16 @@ def partition_cells(mesh: Mesh, nparts: int, method: str = "rcb") -> np.ndarray:
     if nparts <= 1:
         return part
     if method == "rcb":
-        _rcb(mesh.cell_centroids(), np.arange(E), nparts, part, 0)
+        # centroid coordinates, one contiguous array per axis (column reductions over an (E, d) array are slow)
+        nv = mesh.cells.shape[1]
+        cols = []
+        for k in range(mesh.dim):
+            xk = np.ascontiguousarray(mesh.coords[:, k])
+            acc = xk[mesh.cells[:, 0]]
+            for v in range(1, nv):
+                acc = acc + xk[mesh.cells[:, v]]
+            cols.append(acc / nv)
+        _rcb(cols, None, nparts, part, 0)
         return part
     if method == "metis":
         from .partition_metis import metis_partition

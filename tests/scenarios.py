@@ -107,5 +107,8 @@ def pulse_expressions():
 
 
 def pulse_dt(h, p):
-    """min(0.5 h / (2^(p-1) Vp), 1/sigma_max) with Vp = 1, sigma_max = 100."""
-    return min(0.5 * h / (2 ** (p - 1) * 1.0), 1.0 / 100.0)
+    """min(0.16 h / (2^(p-1) Vp), 1/sigma_max) with Vp = 1, sigma_max = 100.  SURVEY.md 8d config 3 proposed Courant 0.5
+    "to be confirmed in the oracle before freezing": at the full resolution h = 1/16 the explicit sponge (sigma dt = 1)
+    on top of the wave operator is unstable at P2 for dt > 0.00625 and at P3 for dt > 0.005 (growth 1e40-1e94 in 300
+    steps in the CPU oracle), so the Courant number is 0.16: dt = 0.01 / 0.005 / 0.0025 for P1 / P2 / P3 at h = 1/16."""
+    return min(0.16 * h / (2 ** (p - 1) * 1.0), 1.0 / 100.0)
