@@ -200,7 +200,7 @@ def sample_problem():
     u = 1e-3 * rng.standard_normal((E, nd, 2))
     s = 1e-3 * rng.standard_normal((E, nd, 2, 2))
     ndof = E * nd * 6
-    return co, u, s, orc.dt, ndof, f"Marmousi 2D P{DEGREE} at h=24 m: {E} cells, {ndof} DoF"
+    return co, u, s, orc.dt, ndof, f"Marmousi 2D P{DEGREE} at h=24 m: {E} cells, {ndof} DoF", fused_from(mesh, orc)
 
 
 def host_threads():
@@ -243,7 +243,18 @@ def full_problem_cpu(scale=1.0):
     s0 = 1e-3 * rng.standard_normal((E, nd, 2, 2))
     s = np.ascontiguousarray(0.5 * (s0 + np.swapaxes(s0, 2, 3)))
     ndof = E * nd * 6
-    return co, u, s, src, orc.dt, ndof, f"marmousi_2d_p{DEGREE}_{nx}x{ny}"
+    return co, u, s, src, orc.dt, ndof, f"marmousi_2d_p{DEGREE}_{nx}x{ny}", fused_from(mesh, orc)
+
+
+def fused_from(mesh, orc):
+    """The second CPU baseline of BASELINE.md section 3 for the same problem: the six-pass algorithm the GPU runs, in
+    C/OpenMP (oracle/elastic_fused_c.c)."""
+    from oracle.c_fused import CFused
+    from seigen_b200.refelem import get_refelem
+    el = get_refelem(mesh.dim, orc.p)
+    t = mesh.topology
+    return CFused(el.Dr, el.Lift, el.fnodes, el.ftab, t.nbr, t.code, t.jinv, orc.l, orc.mu, orc.density,
+                  sigma_mats=CFused.sponge_matrices(orc))
 
 
 def profiled_traffic():
@@ -270,8 +281,9 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    co, u, s, src, dt, ndof, wname = full_problem_cpu(args.scale)
+    co, u, s, src, dt, ndof, wname, cf = full_problem_cpu(args.scale)
     cores = co.set_threads(host_threads())          # torchrun exports OMP_NUM_THREADS=1: use every core we may
+    cf.set_threads(cores)
     setup = time.perf_counter() - t0
     # each bench step = one LF4 time step of the full per-GPU mesh (~1 s on 16+ cores); capped so that the whole run
     # stays within a few minutes
@@ -280,6 +292,10 @@ def run_reference(args):
     warm = max(0, min(args.warmup, int(15.0 / max(t_probe, 1e-6))))
     wall = time_cpu(co, u, s, dt, steps, warm, src)
     val = ndof * steps / wall
+    # second CPU baseline (reported beside the first, not instead of it): the fused six-pass algorithm on the host
+    tf = time_cpu(cf, u, s, dt, max(2, steps), 1, src)
+    fused = {"value": ndof * max(2, steps) / tf, "unit": UNIT, "cores": cf.threads, "kind": "port-fused",
+             "note": "the six-pass algorithm the GPU runs (SURVEY.md 8a K1-K6) in C/OpenMP, oracle/elastic_fused_c.c"}
     world = env_int("WORLD_SIZE", 1)
     sample = (f"{wname}: the GPU arm's mesh, degree, per-cell materials, Ricker source and dt for ONE GPU "
               f"({ndof} DoF), {steps} time steps" + ("" if world == 1 else f" -- 1/{world} of the {world}-GPU workload"))
@@ -293,6 +309,7 @@ def run_reference(args):
                               "reference's PyOP2 loop structure (oracle/elastic_c.c: 25 sweeps per step), all host "
                               "threads"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline_fused": fused,
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -498,13 +515,18 @@ def run_gpu(args):
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu and args.workload == "marmousi":
-        co, u, s, cdt, cndof, sample = sample_problem()
+        co, u, s, cdt, cndof, sample, cf = sample_problem()
         co.set_threads(host_threads())
+        cf.set_threads(co.threads)
         t1 = time_cpu(co, u, s, cdt, 1, 1)
         csteps = max(2, min(60, int(15.0 / max(t1, 1e-6))))
         cw = time_cpu(co, u, s, cdt, csteps, 0)
+        fw = time_cpu(cf, u, s, cdt, csteps, 1)
         cpu = {"value": cndof * csteps / cw, "unit": UNIT, "cores": co.threads, "kind": "port",
-               "sample": f"{sample}, {csteps} steps"}
+               "sample": f"{sample}, {csteps} steps",
+               "fused_variant": {"value": cndof * csteps / fw, "unit": UNIT, "cores": cf.threads, "kind": "port-fused",
+                                 "note": "second CPU baseline of BASELINE.md section 3: the six-pass algorithm in "
+                                         "C/OpenMP (oracle/elastic_fused_c.c)"}}
 
     degree, halo_mode, symmetric = int(el.S.degree), el.halo_mode, bool(dev.symmetric)
     # ---- extras: what the headline does not show (3D, strong scaling, the other elements) -------------------------

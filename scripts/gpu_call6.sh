@@ -1,0 +1,9 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r2c6_pytest.log
+for cfg in "2 3 1000 400 1" "2 4 800 300 1" "3 1 128 32 32" "3 2 64 32 32"; do
+  set -- $cfg
+  timeout 400 python scripts/tune_stages.py --dim $1 --degree $2 --nx $3 --ny $4 --nz $5 >> gpurun_out/r2c6_tune.log 2>&1
+done
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2c6_bench.json 2> gpurun_out/r2c6_bench.err

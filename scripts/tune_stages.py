@@ -16,18 +16,17 @@ from seigen_b200.device import DeviceSolver  # noqa: E402
 from seigen_b200.mesh import BoxMesh, RectangleMesh  # noqa: E402
 from seigen_b200.refelem import get_refelem  # noqa: E402
 
-VARIANTS = {   # (tile, split, minb, minba, ns) as compiled in csrc/sg_inst_*.cu
-    (2, 1): [(128, 1, 4, 2, 22), (64, 1, 8, 4, 22)],
-    (2, 2): [(64, 1, 8, 3, 22), (64, 1, 10, 3, 22), (128, 1, 4, 2, 22), (64, 2, 4, 3, 22), (128, 1, 4, 2, 32),
-             (64, 1, 8, 3, 32), (32, 1, 16, 6, 22), (32, 1, 16, 6, 32)],
-    (2, 3): [(32, 1, 8, 4, 22), (64, 1, 4, 2, 22)],
-    (2, 4): [(32, 1, 4, 3, 22)],
-    (3, 1): [(64, 1, 4, 3, 22), (64, 1, 6, 3, 22), (32, 1, 8, 4, 22), (32, 3, 4, 4, 32), (64, 1, 4, 3, 32),
-             (32, 1, 8, 4, 32), (32, 1, 12, 6, 22)],
-    (3, 2): [(32, 3, 3, 3, 22), (32, 3, 4, 4, 22), (32, 3, 3, 3, 32), (64, 3, 2, 2, 22), (32, 1, 4, 4, 22),
-             (32, 3, 5, 4, 22)],
-    (3, 3): [(32, 3, 2, 2, 22), (32, 3, 2, 2, 21), (32, 3, 3, 3, 22), (32, 3, 3, 3, 11), (32, 3, 2, 2, 11),
-             (32, 3, 3, 2, 12)],
+VARIANTS = {   # (tile, split, minb, minba, ns, xreg, axs) as compiled in csrc/sg_inst_*.cu
+    (2, 1): [(128, 1, 4, 2, 22, 1, 1), (64, 1, 8, 4, 22, 1, 1)],
+    (2, 2): [(128, 1, 4, 2, 22, 1, 1), (64, 1, 8, 3, 22, 1, 1), (256, 1, 2, 1, 22, 1, 1)],
+    (2, 3): [(64, 1, 4, 2, 22, 1, 1), (32, 1, 8, 4, 22, 1, 1), (64, 1, 4, 3, 22, 1, 1), (64, 1, 4, 2, 22, 1, 0)],
+    (2, 4): [(32, 2, 3, 3, 22, 0, 1), (32, 1, 4, 3, 22, 0, 1), (64, 2, 2, 2, 22, 0, 1), (32, 2, 4, 3, 22, 0, 1),
+             (32, 2, 3, 3, 22, 0, 0), (32, 1, 4, 3, 22, 1, 0)],
+    (3, 1): [(64, 1, 4, 4, 22, 1, 1), (64, 1, 4, 3, 22, 0, 1), (32, 1, 8, 4, 22, 1, 1), (128, 1, 2, 2, 22, 1, 1),
+             (64, 1, 4, 4, 22, 1, 0), (128, 1, 2, 2, 22, 1, 0), (128, 1, 2, 3, 21, 1, 1)],
+    (3, 2): [(64, 3, 2, 2, 22, 0, 0), (32, 3, 3, 3, 22, 0, 1), (128, 3, 1, 1, 22, 0, 0), (64, 1, 4, 2, 22, 0, 0),
+             (64, 3, 2, 3, 22, 0, 0)],
+    (3, 3): [(32, 3, 2, 2, 22, 0, 0), (32, 3, 2, 2, 21, 0, 0)],
 }
 
 
@@ -49,8 +48,9 @@ def main():
     u = rng.standard_normal((E * el.nd, d)) * 1e-3
     s = rng.standard_normal((E * el.nd, d, d)) * 1e-3
     s = 0.5 * (s + np.swapaxes(s, 1, 2))
-    for tile, split, minb, minba, ns in VARIANTS[(a.dim, a.degree)]:
-        os.environ.update(SG_TILE=str(tile), SG_SPLIT=str(split), SG_MINB=str(minb), SG_MINBA=str(minba), SG_NS=str(ns))
+    for tile, split, minb, minba, ns, xreg, axs in VARIANTS[(a.dim, a.degree)]:
+        os.environ.update(SG_TILE=str(tile), SG_SPLIT=str(split), SG_MINB=str(minb), SG_MINBA=str(minba), SG_NS=str(ns),
+                          SG_XREG=str(xreg), SG_AXS=str(axs))
         dev = DeviceSolver(mesh, a.degree, symmetric=True)
         dev.set_material(1.0, 0.5, 0.25)
         dev.set_state(u, s)
@@ -62,7 +62,7 @@ def main():
         for _ in range(2):
             dev.step(a.steps, dt)
             best = min(best, dev.last_step_ms() / a.steps)
-        print(f"{a.tag} d{d}p{a.degree} tile={tile} split={split} minb={minb}/{minba} ns={ns}: "
+        print(f"{a.tag} d{d}p{a.degree} tile={tile} split={split} minb={minb}/{minba} ns={ns} xreg={xreg} axs={axs}: "
               + " ".join(f"K{k + 1}={1e3 * t:.1f}" for k, t in enumerate(st))
               + f" | step {best:.4f} ms {ndof / best / 1e6:.2f} Gupd/s", flush=True)
         dev.close()

@@ -3,6 +3,8 @@
 #include "sg_kernels.cuh"
 #include "sg_variants.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -15,6 +17,13 @@
 namespace {
 
 thread_local std::string g_err;
+
+// NVTX ranges around the host-side phases (visible in Nsight Systems / filterable in Nsight Compute); the role of the
+// reference's timed_region('timestepping' / 'solver setup' / 'i/o') markers (seigen/elastic.py:76, 247, 278)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -50,12 +59,16 @@ int env_int(const char* name) {
 const Variant* find_variant(int dim, int degree) {
   const int tile = env_int("SG_TILE"), split = env_int("SG_SPLIT"), minb = env_int("SG_MINB"), ns = env_int("SG_NS");
   const int minba = env_int("SG_MINBA");
+  const char* ex = std::getenv("SG_XREG");
+  const char* ea = std::getenv("SG_AXS");
+  const int xreg = ex ? std::atoi(ex) : -1, axs = ea ? std::atoi(ea) : -1;
   const Variant* first = nullptr;
   for (const Variant& v : variants()) {
     if (v.dim != dim || v.degree != degree) continue;
     if (!first) first = &v;
     if ((tile == 0 || v.tile == tile) && (split == 0 || v.split == split) && (minb == 0 || v.minb == minb) &&
-        (minba == 0 || v.minba == minba) && (ns == 0 || v.ns_plain * 10 + v.ns_axpy == ns))
+        (minba == 0 || v.minba == minba) && (ns == 0 || v.ns_plain * 10 + v.ns_axpy == ns) &&
+        (xreg < 0 || v.xreg == xreg) && (axs < 0 || v.axs == axs))
       return &v;
   }
   return first;
@@ -419,6 +432,7 @@ int sg_tile_cells(int dim, int degree) {
 }
 
 int sg_create(sg_solver** out, const sg_mesh_desc* d) {
+  NvtxRange nvtx_range("sg_create");
   if (!out || !d) return fail(SG_EINVAL, "sg_create: null argument");
   *out = nullptr;
   const Variant* v = find_variant(d->dim, d->degree);
@@ -707,6 +721,7 @@ int sg_set_absorption(sg_solver* h, int64_t n, const int64_t* cell, const double
 }
 
 int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nsteps, const double* amp) {
+  NvtxRange nvtx_range("sg_set_source");
   if (!h) return fail(SG_EINVAL, "null solver");
   if (nsrc < 0 || nsteps < 0 || (nsrc > 0 && (!sdof || (nsteps > 0 && !amp))))
     return fail(SG_EINVAL, "sg_set_source: bad arguments");
@@ -789,6 +804,7 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
 }
 
 int sg_set_state(sg_solver* h, const double* u, const double* s) {
+  NvtxRange nvtx_range("sg_set_state");
   if (!h) return fail(SG_EINVAL, "null solver");
   SG_CUDA(cudaSetDevice(h->device));
   // the scratch fields double as staging buffers: they are dead between time steps
@@ -815,6 +831,7 @@ int sg_set_state(sg_solver* h, const double* u, const double* s) {
 }
 
 int sg_get_state(sg_solver* h, double* u, double* s) {
+  NvtxRange nvtx_range("sg_get_state");
   if (!h) return fail(SG_EINVAL, "null solver");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->comm));
@@ -864,6 +881,7 @@ int sg_stage(sg_solver* h, int stage, int part, double dt, int64_t step) {
 }
 
 int sg_step(sg_solver* h, int64_t nsteps, double dt, int64_t first_step) {
+  NvtxRange nvtx_range("sg_step");
   if (!h) return fail(SG_EINVAL, "null solver");
   if (!h->have_material) return fail(SG_ESTATE, "sg_step: call sg_set_material first");
   if (nsteps < 0) return fail(SG_EINVAL, "sg_step: nsteps < 0");
@@ -1077,6 +1095,7 @@ int sg_ipc_export(sg_solver* h, unsigned char* out) {
 }
 
 int sg_peer_connect(sg_solver* h, int32_t npeers, const sg_peer_desc* peers) {
+  NvtxRange nvtx_range("sg_peer_connect");
   if (!h || npeers < 0 || npeers > 16 || (npeers > 0 && !peers)) return fail(SG_EINVAL, "sg_peer_connect: bad arguments");
   SG_CUDA(cudaSetDevice(h->device));
   SG_CUDA(cudaStreamSynchronize(h->stream));

@@ -5,7 +5,14 @@
 #include "sg_variants.h"
 
 void sg_variants_2d_high(std::vector<Variant>& v) {
+  v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, true>());
   v.push_back(make_variant<2, 3, 32, 1, 8, 4, 2, 2, true, true>());
-  v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, false>());
+  v.push_back(make_variant<2, 3, 64, 1, 4, 3, 2, 2, true, true>());
+  v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, false, true>());
+  v.push_back(make_variant<2, 4, 32, 2, 3, 3, 2, 2, true, false>());
   v.push_back(make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>());
+  v.push_back(make_variant<2, 4, 64, 2, 2, 2, 2, 2, true, false>());
+  v.push_back(make_variant<2, 4, 32, 2, 4, 3, 2, 2, true, false>());
+  v.push_back(make_variant<2, 4, 32, 2, 3, 3, 2, 2, false, false>());
+  v.push_back(make_variant<2, 4, 32, 1, 4, 3, 2, 2, false, true>());
 }

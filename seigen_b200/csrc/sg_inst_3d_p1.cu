@@ -5,11 +5,11 @@
 #include "sg_variants.h"
 
 void sg_variants_3d_p1(std::vector<Variant>& v) {
+  v.push_back(make_variant<3, 1, 64, 1, 4, 4, 2, 2, true, true>());
   v.push_back(make_variant<3, 1, 64, 1, 4, 3, 2, 2, true, false>());
-  v.push_back(make_variant<3, 1, 64, 1, 6, 3, 2, 2, true, false>());
   v.push_back(make_variant<3, 1, 32, 1, 8, 4, 2, 2, true, true>());
-  v.push_back(make_variant<3, 1, 32, 3, 4, 4, 3, 2, true, false>());
-  v.push_back(make_variant<3, 1, 64, 1, 4, 3, 3, 2, true, false>());
-  v.push_back(make_variant<3, 1, 32, 1, 8, 4, 3, 2, true, true>());
-  v.push_back(make_variant<3, 1, 32, 1, 12, 6, 2, 2, true, true>());
+  v.push_back(make_variant<3, 1, 128, 1, 2, 2, 2, 2, true, true>());
+  v.push_back(make_variant<3, 1, 64, 1, 4, 4, 2, 2, false, true>());
+  v.push_back(make_variant<3, 1, 128, 1, 2, 2, 2, 2, false, true>());
+  v.push_back(make_variant<3, 1, 128, 1, 2, 3, 2, 1, true, true>());
 }

@@ -5,10 +5,9 @@
 #include "sg_variants.h"
 
 void sg_variants_3d_p2(std::vector<Variant>& v) {
+  v.push_back(make_variant<3, 2, 64, 3, 2, 2, 2, 2, false, false>());
   v.push_back(make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>());
-  v.push_back(make_variant<3, 2, 32, 3, 4, 4, 2, 2, true, false>());
-  v.push_back(make_variant<3, 2, 32, 3, 3, 3, 3, 2, true, false>());
-  v.push_back(make_variant<3, 2, 64, 3, 2, 2, 2, 2, true, false>());
-  v.push_back(make_variant<3, 2, 32, 1, 4, 4, 2, 2, true, false>());
-  v.push_back(make_variant<3, 2, 32, 3, 5, 4, 2, 2, true, false>());
+  v.push_back(make_variant<3, 2, 128, 3, 1, 1, 2, 2, false, false>());
+  v.push_back(make_variant<3, 2, 64, 1, 4, 2, 2, 2, false, false>());
+  v.push_back(make_variant<3, 2, 64, 3, 2, 3, 2, 2, false, false>());
 }

@@ -7,8 +7,4 @@
 void sg_variants_3d_p3(std::vector<Variant>& v) {
   v.push_back(make_variant<3, 3, 32, 3, 2, 2, 2, 2, false, false>());
   v.push_back(make_variant<3, 3, 32, 3, 2, 2, 2, 1, false, false>());
-  v.push_back(make_variant<3, 3, 32, 3, 3, 3, 2, 2, false, false>());
-  v.push_back(make_variant<3, 3, 32, 3, 3, 3, 1, 1, false, false>());
-  v.push_back(make_variant<3, 3, 32, 3, 2, 2, 1, 1, false, false>());
-  v.push_back(make_variant<3, 3, 32, 3, 3, 2, 1, 2, false, false>());
 }

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     // One thread per cell with small elements: all D rows are computed together (volF_all / liftF_all), so that a
     // stress component two rows need (s_ij = s_ji with symmetric storage) is gathered once -- 9 instead of 12
     // neighbour loads per facet node pair in 2D, 6 instead of 9 in 3D.
-    constexpr bool ROWS_FIRST = (SPLIT == 1) && (D * ND <= 24);
+    constexpr bool ROWS_FIRST = (SPLIT == 1) && (D * ND <= 30);
     double accs[ROWS_FIRST ? IPT : 1][ND];
     auto compute = [&](int ii, double* acc) {
       const int i = ig * IPT + ii;

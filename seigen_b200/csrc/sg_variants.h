@@ -7,7 +7,7 @@
 #include "sg_kernels.cuh"
 
 struct Variant {
-  int dim, degree, nd, nfp, tile, split, minb, minba, ns_plain, ns_axpy, axs;
+  int dim, degree, nd, nfp, tile, split, minb, minba, ns_plain, ns_axpy, axs, xreg;
   // [0]: full stress storage (D*D components), [1]: symmetric storage (upper triangle)
   sg::StagePlan (*plan_f[2])(bool classes, bool mat, bool sponge);
   sg::StagePlan (*plan_f_axpy[2])(bool classes, bool mat, bool sponge);
@@ -51,6 +51,7 @@ inline Variant make_variant() {
   v.ns_plain = NSP;
   v.ns_axpy = NSA;
   v.axs = AXS;
+  v.xreg = XREG;
   fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, false>(v);
   fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, true>(v);
   return v;
