@@ -100,6 +100,10 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
  * [n_owned*nd][d][d] (owned cells; halo cells are filled by the halo exchange).  Either pointer may be NULL (field
  * left unchanged). */
 int sg_set_state(sg_solver* h, const double* u, const double* s);
+/* The same in two halves, so that host-side setup (material / source tables) can run while the state crosses PCIe:
+ * _async queues the copies (the host arrays must stay untouched until _finish), _finish waits and reports SG_EASYM. */
+int sg_set_state_async(sg_solver* h, const double* u, const double* s);
+int sg_set_state_finish(sg_solver* h);
 /* u1.dat.data / s1.dat.data after run (elastic.py:315), owned cells.  Synchronises with all queued work. */
 int sg_get_state(sg_solver* h, double* u, double* s);
 int sg_get_field(sg_solver* h, int which, double* out);

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "sg_set_absorption": (C.c_int, [_P, C.c_int64, _P, _P]),
     "sg_set_source": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P]),
     "sg_set_state": (C.c_int, [_P, _P, _P]),
+    "sg_set_state_async": (C.c_int, [_P, _P, _P]),
+    "sg_set_state_finish": (C.c_int, [_P]),
     "sg_get_state": (C.c_int, [_P, _P, _P]),
     "sg_get_field": (C.c_int, [_P, C.c_int, _P]),
     "sg_step": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int64]),

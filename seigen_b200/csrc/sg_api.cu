@@ -260,7 +260,7 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
     p.timeout_cycles = h->timeout_cycles;
   }
   if (nt > 0) {
-    const int nthreads = v->tile * v->split;
+    const int nthreads = v->threads[occ - h->occ];
     if (h->occ_smem[occ - h->occ] != pl.total) {   // (re)size the kernel's shared memory and its persistent grid
       SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
       SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -663,11 +663,12 @@ int sg_set_material(sg_solver* h, double density, double lam, double mu, const d
   if ((lam_cell == nullptr) != (mu_cell == nullptr))
     return fail(SG_EINVAL, "sg_set_material: give both per-cell arrays or neither");
   SG_CUDA(cudaSetDevice(h->device));
-  SG_CUDA(cudaStreamSynchronize(h->stream));
   const bool per_cell = lam_cell != nullptr;
   const double* old_mat = h->mat.p;
   bool changed = !h->have_material || per_cell != h->per_cell || density != h->density ||
                  (!per_cell && (lam != h->lam_c || mu != h->mu_c));
+  if (!changed && !per_cell) return SG_OK;          // same scalars again: nothing queued work could observe
+  SG_CUDA(cudaStreamSynchronize(h->stream));
   h->density = density;
   h->lam_c = lam;
   h->mu_c = mu;
@@ -694,8 +695,8 @@ int sg_set_absorption(sg_solver* h, int64_t n, const int64_t* cell, const double
   if (!h) return fail(SG_EINVAL, "null solver");
   if (n < 0 || (n > 0 && (!cell || !mats))) return fail(SG_EINVAL, "sg_set_absorption: bad arguments");
   SG_CUDA(cudaSetDevice(h->device));
-  SG_CUDA(cudaStreamSynchronize(h->stream));
   if (n == 0 && h->nabs_pad == 0) return SG_OK;
+  SG_CUDA(cudaStreamSynchronize(h->stream));
   h->config_version++;
   if (n == 0) {
     h->nabs_pad = 0;
@@ -726,8 +727,8 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
   if (nsrc < 0 || nsteps < 0 || (nsrc > 0 && (!sdof || (nsteps > 0 && !amp))))
     return fail(SG_EINVAL, "sg_set_source: bad arguments");
   SG_CUDA(cudaSetDevice(h->device));
-  SG_CUDA(cudaStreamSynchronize(h->stream));
   if ((nsrc == 0 || nsteps == 0) && h->nsrc == 0) return SG_OK;
+  SG_CUDA(cudaStreamSynchronize(h->stream));
   h->config_version++;
   h->nsrc = 0;
   h->src_steps = 0;
@@ -803,7 +804,7 @@ int sg_set_source(sg_solver* h, int64_t nsrc, const int64_t* sdof, int64_t nstep
   return SG_OK;
 }
 
-int sg_set_state(sg_solver* h, const double* u, const double* s) {
+int sg_set_state_async(sg_solver* h, const double* u, const double* s) {
   NvtxRange nvtx_range("sg_set_state");
   if (!h) return fail(SG_EINVAL, "null solver");
   SG_CUDA(cudaSetDevice(h->device));
@@ -818,8 +819,14 @@ int sg_set_state(sg_solver* h, const double* u, const double* s) {
     int rc = relayout(h, h->s.p, h->sh.p, h->dim * h->dim, true, h->stream, h->n_owned);
     if (rc) return rc;
   }
+  return SG_OK;
+}
+
+int sg_set_state_finish(sg_solver* h) {
+  if (!h) return fail(SG_EINVAL, "null solver");
+  SG_CUDA(cudaSetDevice(h->device));
   unsigned int asym = 0;
-  if (s && h->sym) {
+  if (h->sym) {
     SG_CUDA(cudaMemcpyAsync(&asym, h->asym.p, sizeof(asym), cudaMemcpyDeviceToHost, h->stream));
     SG_CUDA(cudaMemsetAsync(h->asym.p, 0, sizeof(asym), h->stream));
   }
@@ -828,6 +835,11 @@ int sg_set_state(sg_solver* h, const double* u, const double* s) {
     return fail(SG_EASYM, "sg_set_state: the stress handed in is not symmetric but the solver was created with "
                           "symmetric_stress = 1; create it with symmetric_stress = 0");
   return SG_OK;
+}
+
+int sg_set_state(sg_solver* h, const double* u, const double* s) {
+  const int rc = sg_set_state_async(h, u, s);
+  return rc ? rc : sg_set_state_finish(h);
 }
 
 int sg_get_state(sg_solver* h, double* u, double* s) {
@@ -959,8 +971,8 @@ int sg_set_receivers(sg_solver* h, int64_t n, const int64_t* cell, const double*
   if (!h) return fail(SG_EINVAL, "null solver");
   if (n < 0 || max_steps < 0 || (n > 0 && (!cell || !weights))) return fail(SG_EINVAL, "sg_set_receivers: bad arguments");
   SG_CUDA(cudaSetDevice(h->device));
-  SG_CUDA(cudaStreamSynchronize(h->stream));
   if (n == 0 && h->nrec == 0) return SG_OK;
+  SG_CUDA(cudaStreamSynchronize(h->stream));
   h->config_version++;
   h->nrec = 0;
   h->rec_steps = 0;

@@ -5,14 +5,18 @@
 #include "sg_variants.h"
 
 void sg_variants_2d_high(std::vector<Variant>& v) {
+  v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, false, true>());
   v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, true>());
   v.push_back(make_variant<2, 3, 32, 1, 8, 4, 2, 2, true, true>());
-  v.push_back(make_variant<2, 3, 64, 1, 4, 3, 2, 2, true, true>());
-  v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, false, true>());
-  v.push_back(make_variant<2, 4, 32, 2, 3, 3, 2, 2, true, false>());
-  v.push_back(make_variant<2, 4, 32, 1, 4, 3, 2, 2, true, false>());
-  v.push_back(make_variant<2, 4, 64, 2, 2, 2, 2, 2, true, false>());
-  v.push_back(make_variant<2, 4, 32, 2, 4, 3, 2, 2, true, false>());
-  v.push_back(make_variant<2, 4, 32, 2, 3, 3, 2, 2, false, false>());
-  v.push_back(make_variant<2, 4, 32, 1, 4, 3, 2, 2, false, true>());
+  {
+    // 2D P4, TILE 32: F-type plain and G-type plain passes with one thread per cell (gradients in registers), the
+    // AXPY passes with one tensor row per thread (K3 staged through shared memory, K6 straight from L2)
+    const Variant one = make_variant<2, 4, 32, 1, 4, 3, 2, 2, false, true>();
+    const Variant rows_staged = make_variant<2, 4, 32, 2, 3, 3, 2, 2, true, false>();
+    const Variant rows_direct = make_variant<2, 4, 32, 2, 3, 3, 2, 2, false, false>();
+    v.push_back(compose_variant(one, rows_staged, one, rows_direct, 12));
+    v.push_back(rows_direct);
+    v.push_back(one);
+    v.push_back(rows_staged);
+  }
 }

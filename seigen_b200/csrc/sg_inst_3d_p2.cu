@@ -5,9 +5,14 @@
 #include "sg_variants.h"
 
 void sg_variants_3d_p2(std::vector<Variant>& v) {
-  v.push_back(make_variant<3, 2, 64, 3, 2, 2, 2, 2, false, false>());
+  {
+    // 3D P2, TILE 64: F-type plain pass with one thread per cell (all rows together: each stress component of a
+    // neighbour gathered once), everything else with one tensor row per thread; AXPY operands straight from L2
+    const Variant rows = make_variant<3, 2, 64, 3, 2, 2, 2, 2, false, false>();
+    const Variant one = make_variant<3, 2, 64, 1, 4, 2, 2, 2, false, false>();
+    v.push_back(compose_variant(one, rows, rows, rows, 13));
+    v.push_back(rows);
+    v.push_back(one);
+  }
   v.push_back(make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>());
-  v.push_back(make_variant<3, 2, 128, 3, 1, 1, 2, 2, false, false>());
-  v.push_back(make_variant<3, 2, 64, 1, 4, 2, 2, 2, false, false>());
-  v.push_back(make_variant<3, 2, 64, 3, 2, 3, 2, 2, false, false>());
 }

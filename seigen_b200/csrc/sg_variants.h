@@ -17,6 +17,10 @@ struct Variant {
   const void* f_axpy[2];
   const void* g_plain[2];
   const void* g_axpy[2];
+  // threads per CTA of f_plain, f_axpy, g_plain, g_axpy (TILE * that kernel's SPLIT): the four kernels of a variant
+  // share the tile size (= the field layout) and nothing else, so a variant may take each kernel from a different
+  // instantiation (compose_variant)
+  int threads[4];
 };
 
 // TILE cells per tile, SPLIT threads per cell, MINB / MINBA CTAs per SM the compiler must allow for the plain / AXPY
@@ -52,11 +56,32 @@ inline Variant make_variant() {
   v.ns_axpy = NSA;
   v.axs = AXS;
   v.xreg = XREG;
+  for (int k = 0; k < 4; ++k) v.threads[k] = TILE * SPLIT;
   fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, false>(v);
   fill_variant<D, P, TILE, SPLIT, MINB, MINBA, NSP, NSA, AXS, XREG, true>(v);
   return v;
 }
 
+
+// A variant whose four kernels come from four instantiations with the same tile size (chosen per pass by
+// scripts/tune_stages.py).  `id` distinguishes it from its sources in SG_SPLIT-style selection: it reports split = id.
+inline Variant compose_variant(const Variant& f_plain, const Variant& f_axpy, const Variant& g_plain,
+                               const Variant& g_axpy, int id) {
+  Variant v = f_plain;
+  for (int m = 0; m < 2; ++m) {
+    v.plan_f_axpy[m] = f_axpy.plan_f_axpy[m];
+    v.f_axpy[m] = f_axpy.f_axpy[m];
+    v.plan_g[m] = g_plain.plan_g[m];
+    v.g_plain[m] = g_plain.g_plain[m];
+    v.plan_g_axpy[m] = g_axpy.plan_g_axpy[m];
+    v.g_axpy[m] = g_axpy.g_axpy[m];
+  }
+  v.threads[1] = f_axpy.threads[1];
+  v.threads[2] = g_plain.threads[2];
+  v.threads[3] = g_axpy.threads[3];
+  v.split = id;
+  return v;
+}
 
 // defined in sg_inst_*.cu; each appends its variants (the first entry of a (dim, degree) is the default)
 void sg_variants_2d_low(std::vector<Variant>& v);    // 2D P1, P2

@@ -376,14 +376,33 @@ class ExplicitElasticLF4(ElasticLF4):
         self.receiver_data = out
 
     # -- state transfer ------------------------------------------------------------------------------------------
-    def _upload_state(self):
+    def _begin_upload(self):
+        """Second and later run() calls: queue the state upload before the host-side setup, so that comparing the
+        material tables / rebuilding the source table happens while u0 and s0 cross PCIe.  Returns the solver the
+        copies were queued on (None if there is none yet)."""
+        dev = self._dev
+        if dev is None or self._halo is not None:
+            return None
+        u = self.u0.dat.current_source().data
+        s = self.s0.dat.current_source().data
+        check(lib.sg_set_state_async(dev.handle, ptr(u), ptr(s)))
+        return dev
+
+    def _upload_state(self, queued_on=None):
         # u0 / s0 may be pending copies of u1 / s1 from the previous run(): upload from where the bytes are
         u = self.u0.dat.current_source().data
         s = self.s0.dat.current_source().data
+        started = queued_on is not None and queued_on is self._dev      # (setup may have rebuilt the solver)
+
+        def upload():
+            if started:
+                check(lib.sg_set_state_finish(self._dev.handle))
+            else:
+                check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
         if self._symmetric:
             asym = False
             try:
-                check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+                upload()
             except capi.SgAsymmetric:
                 asym = True
             if self._agree_asymmetric(asym):
@@ -391,7 +410,7 @@ class ExplicitElasticLF4(ElasticLF4):
                 self._setup_once(self._last_times)
                 check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
         else:
-            check(lib.sg_set_state(self._dev.handle, ptr(u), ptr(s)))
+            upload()
         if self._dev.plan.nranks > 1 and self._halo is None:
             check(lib.sg_exchange(self._dev.handle, capi.FIELD_U))
             check(lib.sg_exchange(self._dev.handle, capi.FIELD_S))
@@ -461,10 +480,11 @@ class ExplicitElasticLF4(ElasticLF4):
         """Run the simulation until t = T; returns the final velocity and stress Functions."""
         self.write(self.u1, self.s1, time=0.0)            # initial condition, as elastic.py:273
         times = step_times(T, self.dt) if self.dt else []
+        queued_on = self._begin_upload()
         self.setup(times)
         with timed_region('timestepping'):
             with timed_region('state upload'):
-                self._upload_state()
+                self._upload_state(queued_on)
             dev = self._dev                               # (the upload may have rebuilt it with full stress storage)
             if self.output and len(times):
                 every = max(1, int(self.output_every))

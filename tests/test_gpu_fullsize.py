@@ -92,7 +92,8 @@ def test_explosive_source_shipped_mesh_to_T25_traces_and_ref_c123():
     (tests/golden/oracle_refc_traces.npz) and (ii) REF-C1..3 at the sensors of uy.py:36-43.
 
     What REF-C pins, measured with the CPU oracle (scripts/make_golden_traces.py; same numbers on the GPU): C1 (above
-    the source) agrees to 14 % relative L2 with amplitude ratio 1.05; at C2 / C3 the Rayleigh-wave train has the right
+    the source) agrees to 15 % relative L2 with amplitude ratio 0.97 (mean of the two cells that share the sensor's
+    mesh line; 14 % / 1.04 and 20 % / 0.90 taken singly); at C2 / C3 the Rayleigh-wave train has the right
     arrival time and waveform (correlation 0.97-0.99) but 2.2 x the amplitude of the external solution -- the surface
     wave excited by a source 1 m below the surface is not resolved by nodal interpolation of a 1 m box on an h = 2.5 m
     mesh.  The reference itself only compares by eye (uy.py:46-80); its plot windows for C2 / C3 are +-8e-6."""
@@ -100,7 +101,9 @@ def test_explosive_source_shipped_mesh_to_T25_traces_and_ref_c123():
     Lx, Ly, h = 300.0, 150.0, 2.5
     zt = np.load(os.path.join(GOLDEN, "oracle_refc_traces.npz"))
     interior = [tuple(p) for p in zt["sensors"]]
-    sensors = [(45.0, 149.0), (90.0, 149.0), (140.0, 149.0)]
+    # a DG field is double-valued on the mesh lines x = 45, 90, 140 the reference's sensors sit on (its VTK probe
+    # picks one side): sample 1 cm to either side and average
+    sensors = [(x + dx, 149.0) for x in (45.0, 90.0, 140.0) for dx in (-0.01, 0.01)]
     mesh = RectangleMesh(120, 60, Lx, Ly)
     el = ElasticLF4.create(mesh, "DG", 2, dimension=2, solver="explicit", output=False)
     el.density, el.mu, el.l = 1.0, EXPL_MU, EXPL_LAM
@@ -129,10 +132,11 @@ def test_explosive_source_shipped_mesh_to_T25_traces_and_ref_c123():
     for k, (lo, hi) in enumerate(windows):
         ref = np.interp(tt, zr["t"], zr["uy"][k])
         w = (tt >= lo) & (tt <= hi)
-        sim = -rec[w, 3 + k, 1]
+        sim = -0.5 * (rec[w, 3 + 2 * k, 1] + rec[w, 4 + 2 * k, 1])
         rel = np.linalg.norm(sim - ref[w]) / np.linalg.norm(ref[w])
         stats.append((rel, correlate(sim, ref[w]), (sim @ ref[w]) / (ref[w] @ ref[w])))
+    # measured with the CPU oracle at the same points: C1 (0.154, 0.988, 0.971), C2 (1.30, 0.985, 2.24), C3 (1.29, 0.971, 2.17)
     rel1, corr1, amp1 = stats[0]
-    assert rel1 < 0.2 and corr1 > 0.98 and 0.9 < amp1 < 1.2, stats
+    assert rel1 < 0.18 and corr1 > 0.98 and 0.92 < amp1 < 1.02, stats
     for rel, corr, amp in stats[1:]:
-        assert corr > 0.95 and 1.8 < amp < 2.6, stats
+        assert corr > 0.95 and 1.9 < amp < 2.5, stats
