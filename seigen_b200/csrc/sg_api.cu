@@ -244,6 +244,9 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
   // the device-side step counter (source table index, receivers) advances with the last pass of a step; with
   // receivers a separate kernel does it after they have been sampled
   if (in_step && stage == 6 && h->nsrc > 0 && h->nrec == 0) p.bump = h->step_dev.p;
+  // the trigger at the end of a CTA's tile loop measured as good as or better than at its start for every element
+  // (profiles/r02_pdl_modes.log: 3D P3 54.3 vs 52.1 G, 2D P4 87.1 vs 84.2 G); SG_PDL_EARLY=1 selects the early one
+  p.pdl_late = env_int("SG_PDL_EARLY") ? 0 : 1;
   if (push && h->npeers > 0 && h->push_tiles > 0) {
     // halo exchange of this pass's output fused into the kernel (sg::halo_wait / sg::halo_push)
     const int which = STAGE_OUTPUT[stage];
@@ -566,7 +569,23 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   // (32-72 B of HBM traffic per cell per pass).  Classes are merged only within SG_GEOM_TOL relative.
   bool use_classes = false;
   if (d->geom_classes) {
-    std::unordered_map<std::string, uint16_t> seen;
+    // key = (binary exponent of the largest entry, the d*d entries in units of 2^-36 of it): fixed-size, hashed with
+    // FNV-1a -- no per-cell heap allocation (this loop runs over every owned cell)
+    struct GeoKey {
+      int64_t v[10];
+      bool operator==(const GeoKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+    };
+    struct GeoKeyHash {
+      size_t operator()(const GeoKey& k) const {
+        uint64_t x = 1469598103934665603ull;
+        for (int i = 0; i < 10; ++i) {
+          x ^= (uint64_t)k.v[i];
+          x *= 1099511628211ull;
+        }
+        return (size_t)x;
+      }
+    };
+    std::unordered_map<GeoKey, uint16_t, GeoKeyHash> seen;
     std::vector<double> tab;
     std::vector<uint16_t> gi(npad, 0);
     const size_t max_classes = 4096;
@@ -578,10 +597,9 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
       int ex = 0;
       std::frexp(nrm, &ex);
       const double q = std::ldexp(1.0, ex - 36);   // quantum: 2^-36 of the largest entry (~1.5e-11 relative)
-      int64_t key[10];
-      key[0] = ex;
-      for (int k = 0; k < dd; ++k) key[1 + k] = (int64_t)std::llround(J[k] / q);
-      std::string ks((const char*)key, sizeof(int64_t) * (1 + dd));
+      GeoKey ks{};
+      ks.v[0] = ex;
+      for (int k = 0; k < dd; ++k) ks.v[1 + k] = (int64_t)std::llround(J[k] / q);
       auto it = seen.find(ks);
       uint16_t cls;
       if (it == seen.end()) {

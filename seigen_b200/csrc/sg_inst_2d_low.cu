@@ -10,4 +10,5 @@ void sg_variants_2d_low(std::vector<Variant>& v) {
   v.push_back(make_variant<2, 2, 128, 1, 4, 2, 2, 2, true, true>());
   v.push_back(make_variant<2, 2, 64, 1, 8, 3, 2, 2, true, true>());
   v.push_back(make_variant<2, 2, 256, 1, 2, 1, 2, 2, true, true>());
+  v.push_back(make_variant<2, 2, 32, 1, 16, 6, 2, 2, true, true>());
 }

@@ -72,6 +72,8 @@ struct StageParams {
   unsigned long long* ctl;              // my control words (SG_CTL_*)
   unsigned long long* const* rflag;     // [npeers] my flag slot in each peer's control words
   long long timeout_cycles;
+  int32_t pdl_late;                     // 1: let the next kernel start being scheduled when this CTA is done with its
+                                        // tiles instead of when it starts (programmatic dependent launch)
   int64_t* bump;                        // last pass of a step inside the step graph: the CTA that finishes last
                                         // advances the device-side step counter (nullptr otherwise)
 };
@@ -196,7 +198,7 @@ template <int D, int ND, int NFP, int TILE, int KS, bool SYM = false> struct FCt
   // per-facet state
   const double* nbp;
   const unsigned char* row;
-  double gf[D], cn, co;
+  double gn[D], go[D];        // facet direction times the weight of the neighbour's / the own trace
 
   __device__ __forceinline__ void t(int b, double* t) const {
     double s[D];
@@ -214,32 +216,34 @@ template <int D, int ND, int NFP, int TILE, int KS, bool SYM = false> struct FCt
     const int n = g->nb[f];
     const unsigned c = g->cd[f];
     const bool bnd = (c & 0x80u) != 0;
-    cn = bnd ? 0.0 : 0.5;
-    co = bnd ? 1.0 : 0.5;
+    // numerical trace: (s_nbr + s_own)/2 on interior facets, 0 on exterior ones (free surface); the facet term is
+    // gf . (trace - s_own) = gn . s_nbr + go . s_own with the two weights folded into the facet direction once per facet
+    const double cn = bnd ? 0.0 : 0.5, co = bnd ? -1.0 : -0.5;
     row = sft + (c & 0x7fu) * NFP;
     const int nt = n / TILE, nl = n % TILE;
     nbp = (nt == tile) ? (tileS + nl) : (gIn + (size_t)nt * (KS * TILE) + nl);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
+      double gfj;
       if (f == 0) {
         double a = g->ji[0][j];
 #pragma unroll
         for (int r = 1; r < D; ++r) a += g->ji[r][j];
-        gf[j] = a;
+        gfj = a;
       } else {
-        gf[j] = -g->ji[f - 1][j];
+        gfj = -g->ji[f - 1][j];
       }
+      gn[j] = cn * gfj;
+      go[j] = co * gfj;
     }
   }
   __device__ __forceinline__ double q(int on, int m) const {
     const int nn = row[m];
-    double acc = 0.0;
+    double acc = go[0] * own[coff[0] + on * TILE];
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-      const double o = own[coff[j] + on * TILE];
-      const double v = nbp[coff[j] + nn * TILE];
-      acc = fma(gf[j], cn * v - co * o, acc);
-    }
+    for (int j = 1; j < D; ++j) acc = fma(go[j], own[coff[j] + on * TILE], acc);
+#pragma unroll
+    for (int j = 0; j < D; ++j) acc = fma(gn[j], nbp[coff[j] + nn * TILE], acc);
     return acc;
   }
   // all D rows at once (one thread per cell): each stored stress component is read once
@@ -261,14 +265,19 @@ template <int D, int ND, int NFP, int TILE, int KS, bool SYM = false> struct FCt
   __device__ __forceinline__ void qall(int on, int m, double* q) const {
     constexpr int NC = ncs<D, SYM>();
     const int nn = row[m];
-    double dlt[NC];
+    double vo[NC], vn[NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) dlt[k] = cn * nbp[(k * ND + nn) * TILE] - co * own[(k * ND + on) * TILE];
+    for (int k = 0; k < NC; ++k) {
+      vo[k] = own[(k * ND + on) * TILE];
+      vn[k] = nbp[(k * ND + nn) * TILE];
+    }
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      double acc = 0.0;
+      double acc = go[0] * vo[scomp<D, SYM>(i, 0)];
 #pragma unroll
-      for (int j = 0; j < D; ++j) acc = fma(gf[j], dlt[scomp<D, SYM>(i, j)], acc);
+      for (int j = 1; j < D; ++j) acc = fma(go[j], vo[scomp<D, SYM>(i, j)], acc);
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc = fma(gn[j], vn[scomp<D, SYM>(i, j)], acc);
       q[i] = acc;
     }
   }
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);
   const unsigned char* sft = smem + pl.ftab;
   const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
-  pdl_launch_dependents();
+  if (!p.pdl_late) pdl_launch_dependents();
   cta_setup<NS, NT>(p, pl, smem, E::ftab(), E::FTAB_SIZE, D * D);
   pdl_wait();   // everything above reads tables that no kernel writes; from here on the previous pass's output is read
 
@@ -616,6 +625,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     __syncthreads();   // the stage may be refilled from the next iteration on
     if (btile) halo_push<TILE, NT>(p, tile);
   }
+  if (p.pdl_late) pdl_launch_dependents();
   if (tid == 0) sched_done(p.sched, p.bump);
 }
 
@@ -636,7 +646,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
   const unsigned char* sft = smem + pl.ftab;
   const double* gtab = reinterpret_cast<const double*>(smem + pl.gtab);
   double* sX = reinterpret_cast<double*>(smem + pl.x);
-  pdl_launch_dependents();
+  if (!p.pdl_late) pdl_launch_dependents();
   cta_setup<NS, NT>(p, pl, smem, E::ftab(), E::FTAB_SIZE, D * D);
   pdl_wait();   // (see stage_f_kernel)
 
@@ -762,6 +772,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
       halo_push<TILE, NT>(p, tile);
     }
   }
+  if (p.pdl_late) pdl_launch_dependents();
   if (tid == 0) sched_done(p.sched, p.bump);
 }
 
