@@ -16,6 +16,10 @@ last_json r2c7_box3d.json r02_bench_box3d_n1_pdl.json
 last_json r2c7_box3d_nopdl.json r02_bench_box3d_n1_nopdl.json
 last_json r2c4_bench_ref.json r02_bench_reference_arm.json
 last_json r2c8_n8.json r02_scale_n8.json
+last_json r2c12_n8.json r02_scale_n8_batched_push.json
+last_json r2c12_n1.json r02_scale_n1_same_box_batched_push.json
+last_json r2c11_n2.json r02_bench_n2_batched_push.json
+cat gpurun_out/r2c10_small.log gpurun_out/r2c11_small.log > profiles/r02_small_problem.log 2>/dev/null
 last_json r2c8_n4.json r02_scale_n4.json
 last_json r2c8_n1.json r02_scale_n1_same_box.json
 cp_if r2c8_topo.txt r02_scale_topology.txt

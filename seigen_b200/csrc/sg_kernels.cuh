@@ -463,7 +463,7 @@ __device__ __forceinline__ void wait_flag(unsigned long long* ctl, int slot, uns
       ctl[SG_CTL_ERROR] = 1;
       break;
     }
-    __nanosleep(100);
+    __nanosleep(32);
   }
 }
 
@@ -484,18 +484,31 @@ __device__ __forceinline__ void halo_push(const StageParams& p, int tile) {
   const int lo = p.push_start[tile], n = p.push_start[tile + 1] - lo;
   const int K = p.K_out;
   const double* src = p.out + (size_t)tile * K * TILE;
-  for (int idx = threadIdx.x; idx < n * K; idx += NT) {
-    const int c = lo + idx % n, k = idx / n;
+  // one work item = (cell entry, batch of HB rows): the rows of a batch are loaded together and then stored together,
+  // so an item costs one round trip to L2 instead of HB (this loop sits on the exchange's critical path: the
+  // neighbour's next pass waits for these rows)
+  constexpr int HB = 8;
+  const int nb = (K + HB - 1) / HB;
+  for (int idx = threadIdx.x; idx < n * nb; idx += NT) {
+    const int c = lo + idx % n, k0 = (idx / n) * HB;
     const int64_t r = p.push_dst[c];
-    double* dst = p.rfield[p.push_peer[c]];
-    dst[((r / TILE) * K + k) * TILE + r % TILE] = src[k * TILE + p.push_lane[c]];
+    double* dst = p.rfield[p.push_peer[c]] + ((r / TILE) * K + k0) * TILE + r % TILE;
+    const double* s = src + k0 * TILE + p.push_lane[c];
+    double v[HB];
+#pragma unroll
+    for (int k = 0; k < HB; ++k)
+      if (k0 + k < K) v[k] = s[k * TILE];
+#pragma unroll
+    for (int k = 0; k < HB; ++k)
+      if (k0 + k < K) dst[k * TILE] = v[k];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();                                   // this CTA's remote rows before the count / the flag
     if (atomicAdd(p.sched + 2, 1u) == (unsigned)p.push_tiles - 1u) {
       p.sched[2] = 0u;
-      __threadfence_system();
+      // every other boundary CTA fenced its rows before it counted; the release store below orders this thread's
+      // observation of the count (and with it their rows) before the flag
       const unsigned long long epoch = p.ctl[SG_CTL_SENT] + 1;
       p.ctl[SG_CTL_SENT] = epoch;
       for (int q = 0; q < p.npeers; ++q) st_release_sys(p.rflag[q], epoch);
