@@ -46,7 +46,10 @@ def main():
     u = rng.standard_normal((E * el.nd, d)) * 1e-3
     s = rng.standard_normal((E * el.nd, d, d)) * 1e-3
     s = 0.5 * (s + np.swapaxes(s, 1, 2))
-    for tile, split, minb, minba, ns, xreg, axs in VARIANTS[(a.dim, a.degree)]:
+    variants = VARIANTS[(a.dim, a.degree)]
+    if os.environ.get("SG_ONLY_DEFAULT"):
+        variants = variants[:1]
+    for tile, split, minb, minba, ns, xreg, axs in variants:
         os.environ.update(SG_TILE=str(tile), SG_SPLIT=str(split), SG_MINB=str(minb), SG_MINBA=str(minba), SG_NS=str(ns),
                           SG_XREG=str(xreg), SG_AXS=str(axs))
         dev = DeviceSolver(mesh, a.degree, symmetric=True)

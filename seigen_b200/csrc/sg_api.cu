@@ -247,6 +247,7 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
   // the trigger at the end of a CTA's tile loop measured as good as or better than at its start for every element
   // (profiles/r02_pdl_modes.log: 3D P3 54.3 vs 52.1 G, 2D P4 87.1 vs 84.2 G); SG_PDL_EARLY=1 selects the early one
   p.pdl_late = env_int("SG_PDL_EARLY") ? 0 : 1;
+  p.prefetch = env_int("SG_PREFETCH");
   if (push && h->npeers > 0 && h->push_tiles > 0) {
     // halo exchange of this pass's output fused into the kernel (sg::halo_wait / sg::halo_push)
     const int which = STAGE_OUTPUT[stage];
@@ -261,6 +262,7 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
     p.ctl = h->ctl.p;
     p.rflag = h->rflag.p;
     p.timeout_cycles = h->timeout_cycles;
+    p.dbg = env_int("SG_EXCHANGE_DEBUG");
   }
   if (nt > 0) {
     const int nthreads = v->threads[occ - h->occ];
@@ -270,6 +272,30 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
       int nb = 0;
       SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, nthreads, pl.total));
       if (nb < 1) return fail(SG_ECUDA, "stage kernel does not fit on an SM (shared memory plan too large)");
+      {
+        // Shared memory and L1 share the SM's 256 KB.  The facet gathers of out-of-tile neighbours go through L1, so
+        // give shared memory only what the resident CTAs need (smallest hardware configuration that keeps the
+        // occupancy computed above) and leave the rest to L1: 3D P3 K1 152 -> 127 us, 2D P3 +3 %
+        // (profiles/r02_experiment_l1_prefetch_and_carveout.log).  SG_CARVEOUT=<percent> overrides, 100 = round 1.
+        static const int config_kb[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+        const size_t need = (size_t)nb * (pl.total + 1024);      // 1 KB per CTA is reserved by the system
+        int pick = 228;
+        for (int kb : config_kb)
+          if ((size_t)kb * 1024 >= need) {
+            pick = kb;
+            break;
+          }
+        int carve = (pick * 100 + 227) / 228;
+        if (env_int("SG_CARVEOUT") > 0) carve = env_int("SG_CARVEOUT");
+        if (carve < 100) {
+          SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+          int nb2 = 0;
+          SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, fn, nthreads, pl.total));
+          if (nb2 < nb && env_int("SG_CARVEOUT") == 0)      // the hint would cost occupancy: keep the maximum
+            SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+        }
+      }
       *occ = nb;
       h->occ_smem[occ - h->occ] = pl.total;
     }

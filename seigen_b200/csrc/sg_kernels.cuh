@@ -72,6 +72,9 @@ struct StageParams {
   unsigned long long* ctl;              // my control words (SG_CTL_*)
   unsigned long long* const* rflag;     // [npeers] my flag slot in each peer's control words
   long long timeout_cycles;
+  int32_t dbg;                          // measurement only (SG_EXCHANGE_DEBUG): 1 skip the wait, 2 skip the remote stores,
+                                        // 4 skip the system fence -- results are wrong, timings show what each part costs
+  int32_t prefetch;                     // 1: prefetch the rows of out-of-tile facet neighbours into L1 before the volume part
   int32_t pdl_late;                     // 1: let the next kernel start being scheduled when this CTA is done with its
                                         // tiles instead of when it starts (programmatic dependent launch)
   int64_t* bump;                        // last pass of a step inside the step graph: the CTA that finishes last
@@ -390,6 +393,30 @@ __device__ __forceinline__ void load_geom(const StageParams& p, const StagePlan&
   }
 }
 
+// Facet neighbours outside the tile are read straight from global memory (L2-hot, but ~800 cycles away, and the
+// register budget does not let the compiler hoist these loads above the volume part).  Touching their rows with
+// prefetch.global.L1 as soon as the adjacency of the tile is known turns the later loads into L1 hits: the latency is
+// spent while the volume contraction runs.  NCOMP components x NFP facet nodes per out-of-tile facet, 8 bytes each.
+template <int D, int ND, int NFP, int TILE, int NCOMP>
+__device__ __forceinline__ void prefetch_out_of_tile(const double* gIn, const unsigned char* sft,
+                                                     const FaceGeom<D, ND, NFP, TILE>& g, int tile) {
+#pragma unroll
+  for (int f = 0; f <= D; ++f) {
+    const int n = g.nb[f];
+    const int nt = n / TILE;
+    if (nt != tile) {
+      const unsigned char* row = sft + (g.cd[f] & 0x7fu) * NFP;
+      const double* base = gIn + (size_t)nt * (NCOMP * ND * TILE) + n % TILE;
+#pragma unroll
+      for (int m = 0; m < NFP; ++m) {
+        const double* pn = base + row[m] * TILE;
+#pragma unroll
+        for (int k = 0; k < NCOMP; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + k * ND * TILE));
+      }
+    }
+  }
+}
+
 // CTA-wide setup shared by both kernels: barriers, facet node table, geometry class table
 template <int NS, int NTHREADS>
 __device__ __forceinline__ void cta_setup(const StageParams& p, const StagePlan& pl, unsigned char* smem,
@@ -469,7 +496,7 @@ __device__ __forceinline__ void wait_flag(unsigned long long* ctl, int slot, uns
 
 // Before a CTA reads halo cells: the peers' rows of the last exchange must have landed.  Called by all threads.
 __device__ __forceinline__ void halo_wait(const StageParams& p) {
-  if ((int)threadIdx.x < p.npeers) {
+  if ((int)threadIdx.x < p.npeers && !(p.dbg & 1)) {
     const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(p.ctl + SG_CTL_SENT);
     wait_flag(p.ctl, threadIdx.x, epoch, p.timeout_cycles);
   }
@@ -500,11 +527,11 @@ __device__ __forceinline__ void halo_push(const StageParams& p, int tile) {
       if (k0 + k < K) v[k] = s[k * TILE];
 #pragma unroll
     for (int k = 0; k < HB; ++k)
-      if (k0 + k < K) dst[k * TILE] = v[k];
+      if (k0 + k < K && !(p.dbg & 2)) dst[k * TILE] = v[k];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();                                   // this CTA's remote rows before the count / the flag
+    if (!(p.dbg & 4)) __threadfence_system();                 // this CTA's remote rows before the count / the flag
     if (atomicAdd(p.sched + 2, 1u) == (unsigned)p.push_tiles - 1u) {
       p.sched[2] = 0u;
       // every other boundary CTA fenced its rows before it counted; the release store below orders this thread's
@@ -555,6 +582,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     load_geom<D, ND, NFP, TILE>(p, pl, stage, gtab, lane, g);
     int aidx = -1;
     if (pl.abs_b) aidx = reinterpret_cast<const int32_t*>(stage + pl.abs)[lane];
+    if (p.prefetch && ig == 0) prefetch_out_of_tile<D, ND, NFP, TILE, ncs<D, SYM>()>(p.in, sft, g, tile);
 
     FCtx<D, ND, NFP, TILE, KS, SYM> c;
     c.tileS = sIn;
@@ -685,6 +713,7 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
 
     FaceGeom<D, ND, NFP, TILE> g;
     load_geom<D, ND, NFP, TILE>(p, pl, stage, gtab, lane, g);
+    if (p.prefetch && ig == 0) prefetch_out_of_tile<D, ND, NFP, TILE, D>(p.in, sft, g, tile);
 
     GCtx<D, ND, NFP, TILE> c;
     c.tileU = sIn;
