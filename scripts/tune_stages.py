@@ -13,6 +13,7 @@ import numpy as np
 
 sys.path.insert(0, ".")
 from seigen_b200.device import DeviceSolver  # noqa: E402
+from seigen_b200.layout import build_rank_plan  # noqa: E402
 from seigen_b200.mesh import BoxMesh, RectangleMesh  # noqa: E402
 from seigen_b200.refelem import get_refelem  # noqa: E402
 
@@ -37,8 +38,14 @@ def main():
     ap.add_argument("--nz", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--cube", type=int, default=0, help="3D: UnitCubeMesh(N) (the box3d workload's mesh) instead of the box")
+    ap.add_argument("--fake-intile", action="store_true",
+                    help="measurement only (results are wrong): every out-of-tile facet neighbour is replaced by the cell "
+                         "itself, so all facet gathers hit the shared-memory tile -- the time without any L2 gather")
     a = ap.parse_args()
     mesh = RectangleMesh(a.nx, a.ny, 9192.0, 2904.0) if a.dim == 2 else BoxMesh(a.nx, a.ny, a.nz, 4.0, 1.0, 1.0)
+    if a.dim == 3 and a.cube:
+        mesh = BoxMesh(a.cube, a.cube, a.cube, 1.0, 1.0, 1.0)
     el = get_refelem(a.dim, a.degree)
     E, d = mesh.num_cells(), a.dim
     ndof = E * el.nd * (d + d * d)
@@ -52,7 +59,11 @@ def main():
     for tile, split, minb, minba, ns, xreg, axs in variants:
         os.environ.update(SG_TILE=str(tile), SG_SPLIT=str(split), SG_MINB=str(minb), SG_MINBA=str(minba), SG_NS=str(ns),
                           SG_XREG=str(xreg), SG_AXS=str(axs))
-        dev = DeviceSolver(mesh, a.degree, symmetric=True)
+        plan = build_rank_plan(mesh, np.zeros(E, dtype=np.int32), 0, 1)
+        if a.fake_intile:
+            me = np.arange(plan.n_owned, dtype=plan.nbr.dtype)[:, None]
+            plan.nbr = np.ascontiguousarray(np.where(plan.nbr // tile == me // tile, plan.nbr, me))
+        dev = DeviceSolver(mesh, a.degree, symmetric=True, plan=plan)
         dev.set_material(1.0, 0.5, 0.25)
         dev.set_state(u, s)
         dt = 1e-6

@@ -247,7 +247,6 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
   // the trigger at the end of a CTA's tile loop measured as good as or better than at its start for every element
   // (profiles/r02_pdl_modes.log: 3D P3 54.3 vs 52.1 G, 2D P4 87.1 vs 84.2 G); SG_PDL_EARLY=1 selects the early one
   p.pdl_late = env_int("SG_PDL_EARLY") ? 0 : 1;
-  p.prefetch = env_int("SG_PREFETCH");
   if (push && h->npeers > 0 && h->push_tiles > 0) {
     // halo exchange of this pass's output fused into the kernel (sg::halo_wait / sg::halo_push)
     const int which = STAGE_OUTPUT[stage];

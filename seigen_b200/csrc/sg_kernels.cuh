@@ -74,7 +74,6 @@ struct StageParams {
   long long timeout_cycles;
   int32_t dbg;                          // measurement only (SG_EXCHANGE_DEBUG): 1 skip the wait, 2 skip the remote stores,
                                         // 4 skip the system fence -- results are wrong, timings show what each part costs
-  int32_t prefetch;                     // 1: prefetch the rows of out-of-tile facet neighbours into L1 before the volume part
   int32_t pdl_late;                     // 1: let the next kernel start being scheduled when this CTA is done with its
                                         // tiles instead of when it starts (programmatic dependent launch)
   int64_t* bump;                        // last pass of a step inside the step graph: the CTA that finishes last
@@ -202,6 +201,11 @@ template <int D, int ND, int NFP, int TILE, int KS, bool SYM = false> struct FCt
   const double* nbp;
   const unsigned char* row;
   double gn[D], go[D];        // facet direction times the weight of the neighbour's / the own trace
+  // qall of the largest all-rows kernel (3D P2, 255 registers) forms the weighted jump of each stored component first:
+  // NC values live instead of 2 NC, 3 flops more per facet node, K1 130 -> 124 us (profiles/r02_experiment_qall_forms.log);
+  // everywhere else the folded weights are as fast or faster
+  static constexpr bool QALL_DELTA = (D == 3 && D * ND >= 30);
+  double gf[D], cn1, co1;     // unfolded facet direction and weights (QALL_DELTA)
 
   __device__ __forceinline__ void t(int b, double* t) const {
     double s[D];
@@ -238,6 +242,11 @@ template <int D, int ND, int NFP, int TILE, int KS, bool SYM = false> struct FCt
       }
       gn[j] = cn * gfj;
       go[j] = co * gfj;
+      if (QALL_DELTA) gf[j] = gfj;
+    }
+    if (QALL_DELTA) {
+      cn1 = cn;
+      co1 = co;
     }
   }
   __device__ __forceinline__ double q(int on, int m) const {
@@ -268,6 +277,19 @@ template <int D, int ND, int NFP, int TILE, int KS, bool SYM = false> struct FCt
   __device__ __forceinline__ void qall(int on, int m, double* q) const {
     constexpr int NC = ncs<D, SYM>();
     const int nn = row[m];
+    if (QALL_DELTA) {
+      double dlt[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) dlt[k] = fma(cn1, nbp[(k * ND + nn) * TILE], co1 * own[(k * ND + on) * TILE]);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = gf[0] * dlt[scomp<D, SYM>(i, 0)];
+#pragma unroll
+        for (int j = 1; j < D; ++j) acc = fma(gf[j], dlt[scomp<D, SYM>(i, j)], acc);
+        q[i] = acc;
+      }
+      return;
+    }
     double vo[NC], vn[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
@@ -390,30 +412,6 @@ __device__ __forceinline__ void load_geom(const StageParams& p, const StagePlan&
   for (int f = 0; f < NF; ++f) {
     g.nb[f] = nb[f * TILE];
     g.cd[f] = cd[f * TILE];
-  }
-}
-
-// Facet neighbours outside the tile are read straight from global memory (L2-hot, but ~800 cycles away, and the
-// register budget does not let the compiler hoist these loads above the volume part).  Touching their rows with
-// prefetch.global.L1 as soon as the adjacency of the tile is known turns the later loads into L1 hits: the latency is
-// spent while the volume contraction runs.  NCOMP components x NFP facet nodes per out-of-tile facet, 8 bytes each.
-template <int D, int ND, int NFP, int TILE, int NCOMP>
-__device__ __forceinline__ void prefetch_out_of_tile(const double* gIn, const unsigned char* sft,
-                                                     const FaceGeom<D, ND, NFP, TILE>& g, int tile) {
-#pragma unroll
-  for (int f = 0; f <= D; ++f) {
-    const int n = g.nb[f];
-    const int nt = n / TILE;
-    if (nt != tile) {
-      const unsigned char* row = sft + (g.cd[f] & 0x7fu) * NFP;
-      const double* base = gIn + (size_t)nt * (NCOMP * ND * TILE) + n % TILE;
-#pragma unroll
-      for (int m = 0; m < NFP; ++m) {
-        const double* pn = base + row[m] * TILE;
-#pragma unroll
-        for (int k = 0; k < NCOMP; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + k * ND * TILE));
-      }
-    }
   }
 }
 
@@ -582,7 +580,6 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_f_kernel(const StageP
     load_geom<D, ND, NFP, TILE>(p, pl, stage, gtab, lane, g);
     int aidx = -1;
     if (pl.abs_b) aidx = reinterpret_cast<const int32_t*>(stage + pl.abs)[lane];
-    if (p.prefetch && ig == 0) prefetch_out_of_tile<D, ND, NFP, TILE, ncs<D, SYM>()>(p.in, sft, g, tile);
 
     FCtx<D, ND, NFP, TILE, KS, SYM> c;
     c.tileS = sIn;
@@ -713,7 +710,6 @@ __global__ void __launch_bounds__(TILE* SPLIT, MINB) stage_g_kernel(const StageP
 
     FaceGeom<D, ND, NFP, TILE> g;
     load_geom<D, ND, NFP, TILE>(p, pl, stage, gtab, lane, g);
-    if (p.prefetch && ig == 0) prefetch_out_of_tile<D, ND, NFP, TILE, D>(p.in, sft, g, tile);
 
     GCtx<D, ND, NFP, TILE> c;
     c.tileU = sIn;
