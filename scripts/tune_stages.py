@@ -19,12 +19,13 @@ from seigen_b200.refelem import get_refelem  # noqa: E402
 
 VARIANTS = {   # (tile, split, minb, minba, ns, xreg, axs) as compiled in csrc/sg_inst_*.cu; split >= 11: composed variant
     (2, 1): [(128, 1, 4, 2, 22, 1, 1), (64, 1, 8, 4, 22, 1, 1)],
-    (2, 2): [(128, 1, 4, 2, 22, 1, 1), (64, 1, 8, 3, 22, 1, 1), (256, 1, 2, 1, 22, 1, 1)],
-    (2, 3): [(64, 1, 4, 2, 22, 1, 0), (64, 1, 4, 2, 22, 1, 1), (32, 1, 8, 4, 22, 1, 1)],
+    (2, 2): [(128, 1, 4, 4, 21, 1, 1), (128, 1, 4, 2, 22, 1, 1), (128, 1, 4, 3, 22, 1, 0), (64, 1, 8, 3, 22, 1, 1),
+             (256, 1, 2, 1, 22, 1, 1)],
+    (2, 3): [(64, 1, 4, 3, 21, 1, 1), (64, 1, 4, 2, 22, 1, 0), (64, 1, 4, 2, 22, 1, 1), (32, 1, 8, 4, 22, 1, 1)],
     (2, 4): [(32, 12, 4, 3, 22, 1, 0), (32, 2, 3, 3, 22, 0, 0), (32, 1, 4, 3, 22, 1, 0), (32, 2, 3, 3, 22, 0, 1)],
     (3, 1): [(128, 11, 2, 2, 22, 1, 1), (128, 1, 2, 2, 22, 1, 1), (128, 1, 2, 3, 21, 1, 1), (64, 1, 4, 4, 22, 1, 1),
              (32, 1, 8, 4, 22, 1, 1)],
-    (3, 2): [(64, 13, 4, 2, 22, 0, 0), (64, 3, 2, 2, 22, 0, 0), (64, 1, 4, 2, 22, 0, 0), (32, 3, 3, 3, 22, 0, 1)],
+    (3, 2): [(64, 3, 2, 2, 22, 0, 0), (64, 13, 4, 2, 22, 0, 0), (64, 1, 4, 2, 22, 0, 0), (32, 3, 3, 3, 22, 0, 1)],
     (3, 3): [(32, 3, 2, 2, 22, 0, 0), (32, 3, 2, 2, 21, 0, 0)],
 }
 

@@ -5,6 +5,9 @@
 #include "sg_variants.h"
 
 void sg_variants_2d_high(std::vector<Variant>& v) {
+  // 2D P3, TILE 64: AXPY passes single-stage with 3 CTAs per SM, operands staged through shared memory (K3 94.9 us,
+  // K6 111.1 us; two stages + operands straight from L2: 98.8 / 123.2 us; profiles/r02_tune_axpy_operands.log)
+  v.push_back(make_variant<2, 3, 64, 1, 4, 3, 2, 1, true, true>());
   v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, false, true>());
   v.push_back(make_variant<2, 3, 64, 1, 4, 2, 2, 2, true, true>());
   v.push_back(make_variant<2, 3, 32, 1, 8, 4, 2, 2, true, true>());

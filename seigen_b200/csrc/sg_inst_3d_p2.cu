@@ -6,12 +6,14 @@
 
 void sg_variants_3d_p2(std::vector<Variant>& v) {
   {
-    // 3D P2, TILE 64: F-type plain pass with one thread per cell (all rows together: each stress component of a
-    // neighbour gathered once), everything else with one tensor row per thread; AXPY operands straight from L2
+    // 3D P2, TILE 64: one tensor row per thread in every pass, AXPY operands straight from L2.  (With tiles aligned
+    // to the mesh lattice K1/K5 take 107 us this way and 125 us with one thread per cell and all rows together --
+    // the order was the other way round, 124 against 110 us, on the unaligned Hilbert tiles of the first sweeps;
+    // profiles/r02_tune_axpy_operands.log.)
     const Variant rows = make_variant<3, 2, 64, 3, 2, 2, 2, 2, false, false>();
     const Variant one = make_variant<3, 2, 64, 1, 4, 2, 2, 2, false, false>();
-    v.push_back(compose_variant(one, rows, rows, rows, 13));
     v.push_back(rows);
+    v.push_back(compose_variant(one, rows, rows, rows, 13));
     v.push_back(one);
   }
   v.push_back(make_variant<3, 2, 32, 3, 3, 3, 2, 2, true, false>());
