@@ -195,9 +195,12 @@ class Function:
             return self.assign(expression)
         if not isinstance(expression, Expression):
             expression = Expression(expression)
-        if tuple(expression.value_shape()) != tuple(self._fs.shape):
+        eshape, fshape = tuple(expression.value_shape()), tuple(self._fs.shape)
+        if eshape != fshape and not (eshape == () and all(n == 1 for n in fshape)):
             raise ValueError(f"interpolate: expression shape {expression.value_shape()} != space shape {self._fs.shape}")
-        self.dat.data[...] = expression.evaluate(self._fs.node_coords())
+        # (a scalar expression fills the one-component vector / tensor spaces of a 1-D problem:
+        #  tests/pulse/pulse_1d_lf4.py:27-30)
+        self.dat.data[...] = np.asarray(expression.evaluate(self._fs.node_coords())).reshape(self.dat.data.shape)
         return self
 
     def copy(self, deepcopy=True):

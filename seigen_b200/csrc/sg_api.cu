@@ -41,6 +41,7 @@ int fail(int code, const std::string& msg) {
 const std::vector<Variant>& variants() {
   static const std::vector<Variant> v = [] {
     std::vector<Variant> t;
+    sg_variants_1d(t);
     sg_variants_2d_low(t);
     sg_variants_2d_high(t);
     sg_variants_3d_p1(t);
@@ -464,7 +465,7 @@ int sg_create(sg_solver** out, const sg_mesh_desc* d) {
   if (!out || !d) return fail(SG_EINVAL, "sg_create: null argument");
   *out = nullptr;
   const Variant* v = find_variant(d->dim, d->degree);
-  if (!v) return fail(SG_EINVAL, "sg_create: unsupported (dim, degree); supported: 2D P1-P4, 3D P1-P3");
+  if (!v) return fail(SG_EINVAL, "sg_create: unsupported (dim, degree); supported: 1D P1-P3, 2D P1-P4, 3D P1-P3");
   if (d->n_owned <= 0 || d->n_total < d->n_owned || !d->nbr || !d->code || !d->jinv)
     return fail(SG_EINVAL, "sg_create: bad mesh description");
   if (d->n_boundary < 0 || d->n_boundary > d->n_owned) return fail(SG_EINVAL, "sg_create: bad n_boundary");

@@ -17,6 +17,9 @@
 #include <cuda_runtime.h>
 
 template <int D, int P> struct ElemOps;   // specialised by the generated headers
+#include "gen/elem_d1p1.cuh"
+#include "gen/elem_d1p2.cuh"
+#include "gen/elem_d1p3.cuh"
 #include "gen/elem_d2p1.cuh"
 #include "gen/elem_d2p2.cuh"
 #include "gen/elem_d2p3.cuh"

@@ -84,6 +84,7 @@ inline Variant compose_variant(const Variant& f_plain, const Variant& f_axpy, co
 }
 
 // defined in sg_inst_*.cu; each appends its variants (the first entry of a (dim, degree) is the default)
+void sg_variants_1d(std::vector<Variant>& v);        // 1D P1-P3 (tests/pulse/pulse_1d_lf4.py)
 void sg_variants_2d_low(std::vector<Variant>& v);    // 2D P1, P2
 void sg_variants_2d_high(std::vector<Variant>& v);   // 2D P3, P4
 void sg_variants_3d_p1(std::vector<Variant>& v);

@@ -26,7 +26,7 @@ def _problem(dim, p, symmetric, unstructured=False):
         from tests.test_partition import delaunay_mesh
         mesh = delaunay_mesh(700, seed=9)
     else:
-        mesh = small_mesh(dim, n=12 if dim == 2 else 4)
+        mesh = small_mesh(dim, n={1: 300, 2: 12, 3: 4}[dim])
     from seigen_b200.refelem import get_refelem
     nd = get_refelem(dim, p).nd
     rng = np.random.default_rng(5)
@@ -88,6 +88,7 @@ CASES = [
     (2, 3, 2, True, {}, False),
     (2, 2, 3, True, {"SG_PARTITION": "metis"}, True),            # graph partitioner on a Delaunay mesh
     (2, 2, 2, True, {"SG_PEER_SCHED_SPLIT": "1"}, False),        # the two-stream schedule (comparison path)
+    (1, 2, 2, True, {}, False),                                  # 1-D (tests/pulse/pulse_1d_lf4.py): a facet is a point
 ]
 
 

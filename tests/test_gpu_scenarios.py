@@ -222,3 +222,32 @@ def test_pulse_3d_parity(p):
     assert np.abs(u).max() < 10.0                                  # stable
     assert rel_err(u1.dat.data.reshape(u.shape), u) < 1e-10
     assert rel_err(s1.dat.data.reshape(s.shape), s) < 1e-10
+
+
+def test_pulse_1d_through_the_public_api():
+    """tests/pulse/pulse_1d_lf4.py:7-33 (IntervalMesh(400, 4.0), DG P1, dimension=1, DG1 sponge sigma = 100, scalar
+    Gaussian ICs, dt = 0.0025, T = 2 => 800 steps) through ElasticLF4.run on the device, against the literal oracle."""
+    from oracle.elastic_oracle import ElasticOracle
+    from seigen_b200 import ElasticLF4, Expression, Function, FunctionSpace, IntervalMesh
+    mesh = IntervalMesh(int(4.0 / 1e-2), 4.0)
+    el = ElasticLF4.create(mesh, "DG", 1, dimension=1, output=False)
+    el.density, el.dt, el.mu, el.l = 1.0, 0.0025, 0.25, 0.5
+    el.absorption_function = Function(FunctionSpace(el.mesh, "DG", 1))
+    el.absorption = Expression("x[0] >= 3.5 || x[0] <= 0.5 ? 100.0 : 0")
+    el.u0.assign(Function(el.U).interpolate(Expression('exp(-50*pow((x[0]-1), 2))')))
+    el.s0.assign(Function(el.S).interpolate(Expression('-exp(-50*pow((x[0]-1), 2))')))
+    u0, s0 = el.u0.dat.data.copy(), el.s0.dat.data.copy()
+    u1, s1 = el.run(2.0)
+    assert el.steps_done == 800
+
+    order = el.S.cell_order
+    orc = ElasticOracle(mesh.coords, mesh.cells[order], 1, sigma_degree=1)
+    orc.l, orc.mu, orc.density, orc.dt = 0.5, 0.25, 1.0, 0.0025
+    orc.sigma = el.absorption_function.dat.data.reshape(orc.E, -1)
+    u, s = u0.reshape(orc.E, orc.nd, 1), s0.reshape(orc.E, orc.nd, 1, 1)
+    for _ in range(800):
+        u, s, _ = orc.step(u, s, 0.0)
+    assert rel_err(u1.dat.data.reshape(u.shape), u) < 1e-10
+    assert rel_err(s1.dat.data.reshape(s.shape), s) < 1e-10
+    x = el.U.node_coords()[:, 0]
+    assert abs(x[np.argmax(u1.dat.data[:, 0])] - 3.0) <= 0.02     # the right-going pulse has moved from x = 1 to x = 3

@@ -3,12 +3,14 @@ import numpy as np
 
 from oracle.elastic_oracle import ElasticOracle
 from oracle.nodal import NodalOperator
-from seigen_b200.mesh import BoxMesh, RectangleMesh, perturb_vertices
+from seigen_b200.mesh import BoxMesh, IntervalMesh, RectangleMesh, perturb_vertices
 from seigen_b200.refelem import get_refelem
 
 
 def small_mesh(dim, n=None, perturb=0.15, seed=0):
-    if dim == 2:
+    if dim == 1:
+        m = IntervalMesh(n or 37, 1.7)
+    elif dim == 2:
         n = n or 4
         m = RectangleMesh(n, n + 1, 1.3, 1.0)
     else:
