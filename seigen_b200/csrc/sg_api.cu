@@ -310,6 +310,7 @@ int launch_stage(sg_solver* h, int stage, int part, double dt, cudaStream_t st, 
       grid -= reserve;
     }
     if (grid > nt) grid = nt;
+    if (env_int("SG_GRID_MAX") > 0) grid = std::min(grid, env_int("SG_GRID_MAX"));   // tests: many tiles per CTA on a small mesh
     void* args[] = {(void*)&p};
     if (in_step && env_int("SG_NO_PDL") == 0) {
       // programmatic dependent launch: this kernel's launch + CTA prologue overlap the previous pass's tail
