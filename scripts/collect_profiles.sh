@@ -25,7 +25,7 @@ last_json r2c8_n1.json r02_scale_n1_same_box.json
 cp_if r2c8_topo.txt r02_scale_topology.txt
 [ -f gpurun_out/r2c2_n2_launches.csv ] && python scripts/summarize_ncu.py launches gpurun_out/r2c2_n2_launches.csv profiles/r02_launches_n2_rank0.md > /dev/null
 [ -f gpurun_out/r2_launches.csv ] && python scripts/summarize_ncu.py launches gpurun_out/r2_launches.csv profiles/r02_launches_bench.md > /dev/null
-for n in 2d_p2 3d_p1 3d_p2 3d_p3 2d_p4; do cp_if r2_full_$n.md r02_full_$n.md; done
+for n in 2d_p2 3d_p1 3d_p2 3d_p3 2d_p4 2d_p3; do cp_if r2_full_$n.md r02_full_$n.md; done
 for f in gpurun_out/r2_sanitizer_*.log; do [ -f "$f" ] && cp "$f" profiles/$(basename "$f" | sed 's/^r2_/r02_/'); done
 
 last_json r2c16_bench.json r02_bench_n1_final.json

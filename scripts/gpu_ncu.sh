@@ -7,4 +7,5 @@ scripts/ncu_full.sh r2_full_3d_p1 python scripts/perf_probe.py --dim 3 --degree 
 scripts/ncu_full.sh r2_full_3d_p2 python scripts/perf_probe.py --dim 3 --degree 2 --nx 64 --ny 32 --nz 32 --steps 2 --reps 1
 KEEP_REP=1 scripts/ncu_full.sh r2_full_3d_p3 python scripts/perf_probe.py --dim 3 --degree 3 --nx 64 --ny 32 --nz 16 --steps 2 --reps 1
 scripts/ncu_full.sh r2_full_2d_p4 python scripts/perf_probe.py --dim 2 --degree 4 --nx 800 --ny 300 --steps 2 --reps 1
+scripts/ncu_full.sh r2_full_2d_p3 python scripts/perf_probe.py --dim 2 --degree 3 --nx 1000 --ny 400 --steps 2 --reps 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 20 --warmup 5 --extras none --no-cpu > gpurun_out/r2_ncu_bench.log 2>&1
