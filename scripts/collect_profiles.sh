@@ -28,7 +28,7 @@ cp_if r2c8_topo.txt r02_scale_topology.txt
 for n in 2d_p2 3d_p1 3d_p2 3d_p3 2d_p4 2d_p3; do cp_if r2_full_$n.md r02_full_$n.md; done
 for f in gpurun_out/r2_sanitizer_*.log; do [ -f "$f" ] && cp "$f" profiles/$(basename "$f" | sed 's/^r2_/r02_/'); done
 
-last_json r2c16_bench.json r02_bench_n1_final.json
-last_json r2c16_bench_ref.json r02_bench_reference_arm_final.json
-cp_if r2c16_pytest.log r02_pytest_gpu.log
+last_json r2c29_bench.json r02_bench_n1_final.json
+last_json r2c29_bench_ref.json r02_bench_reference_arm_final.json
+cp_if r2c29_pytest.log r02_pytest_gpu.log
 ls profiles | grep r02
