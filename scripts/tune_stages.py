@@ -60,7 +60,8 @@ def main():
     for tile, split, minb, minba, ns, xreg, axs in variants:
         os.environ.update(SG_TILE=str(tile), SG_SPLIT=str(split), SG_MINB=str(minb), SG_MINBA=str(minba), SG_NS=str(ns),
                           SG_XREG=str(xreg), SG_AXS=str(axs))
-        plan = build_rank_plan(mesh, np.zeros(E, dtype=np.int32), 0, 1)
+        plan = build_rank_plan(mesh, np.zeros(E, dtype=np.int32), 0, 1,
+                               tile=None if os.environ.get("SG_TILE_ORDER") == "0" else tile)
         if a.fake_intile:
             me = np.arange(plan.n_owned, dtype=plan.nbr.dtype)[:, None]
             plan.nbr = np.ascontiguousarray(np.where(plan.nbr // tile == me // tile, plan.nbr, me))

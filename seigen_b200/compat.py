@@ -58,8 +58,31 @@ def _dist():
     return 0, 1
 
 
-def mesh_plan(mesh: Mesh):
-    """The rank plan of ``mesh`` for the current process group (created once per mesh)."""
+def _tile_cells(dim, degree):
+    """Cells per tile of the stage kernels for this element (``sg_tile_cells``), or None: the cell order inside tiles is
+    an optimisation (layout._order_within_tiles), so a missing library or SG_TILE_ORDER=0 only switches it off."""
+    import os
+    if os.environ.get("SG_TILE_ORDER", "1") == "0":
+        return None
+    try:
+        from .capi import lib
+        tile = int(lib.sg_tile_cells(int(dim), int(degree)))
+    except Exception:
+        return None
+    if tile <= 0:
+        return None
+    # measured (profiles/r02_tune_order_within_tiles.log): +0.5 % (2D P2) ... +3 % (3D P1) where one thread owns a whole
+    # cell, -1.5 % for the 3-D elements that run one tensor row per thread in small tiles (3D P2 / P3: TILE 64 / 32) --
+    # there the cells with out-of-tile neighbours end up in the same warps, which then trail the others
+    if dim == 3 and tile < 128:
+        return None
+    return tile
+
+
+def mesh_plan(mesh: Mesh, degree=None):
+    """The rank plan of ``mesh`` for the current process group (created once per mesh, by its first function space:
+    every space on the mesh shares the cell order, which is tuned to the tile size of that first space's degree --
+    ElasticLF4 creates its own spaces before anything else)."""
     plan = getattr(mesh, "_plan", None)
     if plan is None:
         rank, size = _dist()
@@ -69,7 +92,7 @@ def mesh_plan(mesh: Mesh):
             method = os.environ.get("SG_PARTITION") or getattr(mesh, "partition_method", "rcb")
             part = partition_cells(mesh, size, method)
             mesh._partition = part
-        plan = build_rank_plan(mesh, part, rank, size)
+        plan = build_rank_plan(mesh, part, rank, size, tile=_tile_cells(mesh.dim, degree) if degree else None)
         mesh._plan = plan
     return plan
 
@@ -88,7 +111,7 @@ class FunctionSpace:
         self.name = name
         self.shape = tuple(shape)
         self.elem = get_refelem(mesh.dim, self.degree)
-        self.plan = mesh_plan(mesh)
+        self.plan = mesh_plan(mesh, self.degree)
 
     def mesh(self):
         return self.mesh_

@@ -28,7 +28,9 @@ class DeviceSolver:
         self.elem = get_refelem(self.dim, self.degree)
         self.nd = self.elem.nd
         if plan is None:
-            plan = build_rank_plan(mesh, np.zeros(mesh.num_cells(), dtype=np.int32), 0, 1)
+            from .compat import _tile_cells
+            plan = build_rank_plan(mesh, np.zeros(mesh.num_cells(), dtype=np.int32), 0, 1,
+                                   tile=_tile_cells(mesh.dim, degree))
         self.plan = plan
         self._h = C.c_void_p()
         nbr = np.ascontiguousarray(plan.nbr, dtype=np.int32)

@@ -183,10 +183,41 @@ class RankPlan:
         return self.n_total - self.n_owned
 
 
-def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> RankPlan:
+def _order_within_tiles(o_i, n_b, tile, tile_id, topo, cent, bbox, lattice):
+    """Permutation of the interior cells ``o_i`` (positions n_b, n_b + 1, ... of the rank's numbering) that keeps every
+    cell in its tile but puts the cells with a facet neighbour in ANOTHER tile first, grouped by that tile, by the local
+    facet and the gluing code of the facet, and ordered inside a group by the Hilbert key of the point half-way between
+    the two centroids -- a point both sides compute alike.  Consecutive lanes of a tile then read consecutive lanes of
+    the neighbouring tile through the same facet slot: their 8-byte gathers share 32-byte L2 sectors (2.7 lanes per
+    sector instead of 1.3 on the Marmousi grid at TILE 128, 1.4-1.7 instead of 1.15 for Kuhn tetrahedra), and the
+    sectors are what the out-of-tile gathers cost."""
+    n = len(o_i)
+    if n == 0:
+        return o_i
+    my_tile = (n_b + np.arange(n)) // tile
+    nb = topo.nbr[o_i]                                      # (n, nf) sub-mesh indices
+    out = (tile_id[nb] != my_tile[:, None]) & (nb != o_i[:, None])
+    has = out.any(axis=1)
+    first = np.argmax(out, axis=1)                           # lowest local facet that leaves the tile
+    rows = np.arange(n)
+    other = nb[rows, first]
+    grp = np.where(has, tile_id[other], np.iinfo(np.int64).max)
+    fcode = np.where(has, topo.code[o_i][rows, first].astype(np.int64), 0)
+    fidx = np.where(has, first, 0)
+    fkey = np.zeros(n, dtype=np.uint64)
+    if has.any():
+        mid = 0.5 * (cent[o_i[has]] + cent[other[has]])
+        fkey[has] = hilbert_key(mid, bbox=bbox, lattice=lattice)
+    order = np.lexsort((rows, fkey, fcode, fidx, grp, my_tile))
+    return o_i[order]
+
+
+def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int, tile: int | None = None) -> RankPlan:
     """Local numbering of rank ``rank``.  With more than one rank only the sub-mesh made of the owned cells and
     the cells that share a vertex with them (a superset of the facet neighbours) gets its adjacency built, so
-    the cost per rank follows the rank's share of the mesh, not the global mesh."""
+    the cost per rank follows the rank's share of the mesh, not the global mesh.  ``tile``: cells per tile of the
+    kernels that will run on this numbering (``sg_tile_cells``); the interior cells are then also ordered inside
+    their tiles (``_order_within_tiles``) -- an optimisation only, any order is correct."""
     part = np.asarray(part)
     E = mesh.num_cells()
     if nranks > 1:
@@ -217,6 +248,14 @@ def build_rank_plan(mesh: Mesh, part: np.ndarray, rank: int, nranks: int) -> Ran
     o_i = owned[~is_bnd]
     o_b = o_b[np.argsort(key[o_b], kind="stable")]
     o_i = o_i[np.argsort(key[o_i], kind="stable")]
+    if tile:
+        # tile of every cell of the sub-mesh in the numbering built so far: cut-adjacent cells, interior cells, and one
+        # pseudo-tile per owner for the halo cells
+        tile_id = -1 - spart.astype(np.int64)
+        tile_id[o_b] = np.arange(len(o_b)) // tile
+        tile_id[o_i] = (len(o_b) + np.arange(len(o_i))) // tile
+        o_i = _order_within_tiles(o_i, len(o_b), int(tile), tile_id, topo, cent,
+                                  (mesh.coords.min(axis=0), mesh.coords.max(axis=0)), mesh_lattice(mesh))
     owned_sorted = np.concatenate([o_b, o_i])
 
     # halo: remote cells across a facet of an owned cell, grouped by owner, inside a group in the owner's own order of

@@ -90,3 +90,53 @@ def test_one_dimensional_facade_objects():
     assert np.allclose(f.dat.data[:, 0], np.exp(-50 * (x - 1) ** 2))
     with pytest.raises(ValueError):
         Function(el.U).interpolate(Expression(('1.0', '2.0')))
+
+
+def _lanes_per_sector(plan, tile):
+    """Out-of-tile facet gathers per distinct (warp, facet slot, 32-byte sector of the neighbour's row, gluing code):
+    lanes of a warp that read the same sector through the same facet slot cost one L2 request together."""
+    nbr, code = plan.nbr[:plan.n_owned].astype(np.int64), plan.code[:plan.n_owned]
+    E, nf = nbr.shape
+    me = np.arange(E)
+    acc = sec = 0
+    for f in range(nf):
+        n = nbr[:, f]
+        out = (n // tile != me // tile) & (n != me)
+        k = np.stack([me[out] // 32, n[out] // 4, code[out, f].astype(np.int64)], axis=1)
+        acc += int(out.sum())
+        sec += len(np.unique(k, axis=0))
+    return acc / sec
+
+
+@pytest.mark.parametrize("mesh,tile,gain", [(RectangleMesh(200, 96, 1200.0, 576.0), 128, 1.8),
+                                            (BoxMesh(16, 16, 16, 1.0, 1.0, 1.0), 32, 1.15),
+                                            (BoxMesh(16, 16, 8, 2.0, 2.0, 1.0), 64, 1.25)])
+def test_order_within_tiles_shares_sectors_and_keeps_the_tiles(mesh, tile, gain):
+    part = partition_cells(mesh, 1)
+    a = build_rank_plan(mesh, part, 0, 1)
+    b = build_rank_plan(mesh, part, 0, 1, tile=tile)
+    E = mesh.num_cells()
+    ta = np.empty(E, dtype=np.int64)
+    tb = np.empty(E, dtype=np.int64)
+    ta[a.local_to_global] = np.arange(E) // tile
+    tb[b.local_to_global] = np.arange(E) // tile
+    assert np.array_equal(ta, tb)                                    # every cell stays in its tile
+    assert in_tile_fraction(a, tile) == in_tile_fraction(b, tile)
+    assert _lanes_per_sector(b, tile) > gain * _lanes_per_sector(a, tile)
+    # the plan is still a consistent renumbering of the same mesh
+    g = b.local_to_global
+    assert np.array_equal(g[b.nbr], mesh.topology.nbr[g])
+    assert np.array_equal(b.code, mesh.topology.code[g])
+
+
+def test_order_within_tiles_leaves_the_exchange_plan_alone():
+    mesh = RectangleMesh(60, 40, 6.0, 4.0)
+    part = partition_cells(mesh, 3)
+    for r in range(3):
+        a = build_rank_plan(mesh, part, r, 3)
+        b = build_rank_plan(mesh, part, r, 3, tile=64)
+        assert (a.n_owned, a.n_boundary, a.n_total) == (b.n_owned, b.n_boundary, b.n_total)
+        assert np.array_equal(a.local_to_global[:a.n_boundary], b.local_to_global[:b.n_boundary])
+        assert np.array_equal(a.local_to_global[a.n_owned:], b.local_to_global[b.n_owned:])
+        assert np.array_equal(a.send_cells, b.send_cells) and a.recv == b.recv
+        assert np.array_equal(np.sort(a.local_to_global[:a.n_owned]), np.sort(b.local_to_global[:b.n_owned]))
